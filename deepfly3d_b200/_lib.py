@@ -1,0 +1,84 @@
+"""ctypes binding of libdf3d_b200.so (the C ABI declared in include/df3d_b200.h).
+
+There is no fallback: if the shared library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdf3d_b200.so")
+
+DF3D_MAX_CAMS = 8
+
+
+class BAOpts(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("ftol", C.c_double), ("lambda0", C.c_double)]
+
+
+class BAReport(C.Structure):
+    _fields_ = [
+        ("cost0", C.c_double), ("cost", C.c_double), ("lambda_", C.c_double),
+        ("iters", C.c_int32), ("accepted", C.c_int32), ("n_obs", C.c_int32), ("status", C.c_int32),
+    ]
+
+
+class HGDesc(C.Structure):
+    _fields_ = [("num_stacks", C.c_int), ("num_classes", C.c_int), ("in_h", C.c_int), ("in_w", C.c_int),
+                ("max_batch", C.c_int)]
+
+
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/df3d_b200.h one to one
+SIGNATURES = {
+    "df3d_abi_version": (_i, []),
+    "df3d_last_error": (C.c_char_p, []),
+    "df3d_heatmap_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "df3d_heatmap_argmax_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "df3d_pack_points2d": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), _i, _i, _vp, _vp, _vp]),
+    "df3d_triangulate_dlt": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "df3d_projection_matrices": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "df3d_bundle_adjust_workspace_bytes": (_sz, [_i, _i, _i]),
+    "df3d_bundle_adjust": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(BAOpts), _vp, _vp, _vp, _sz, _vp]),
+    "df3d_ba_system_doubles": (_sz, [_i]),
+    "df3d_ba_begin": (_i, [_vp, C.POINTER(BAOpts), _i, _i, _i, _vp, _sz, _vp]),
+    "df3d_ba_linearize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "df3d_ba_solve": (_i, [_i, _vp, _vp, _vp]),
+    "df3d_ba_evaluate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "df3d_ba_decide": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "df3d_ba_end": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "df3d_reprojection_error": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "df3d_hg_param_count": (_sz, [C.POINTER(HGDesc)]),
+    "df3d_hg_workspace_bytes": (_sz, [C.POINTER(HGDesc)]),
+    "df3d_hg_create": (_i, [C.POINTER(HGDesc), _vp, _sz, C.POINTER(_vp)]),
+    "df3d_hg_destroy": (None, [_vp]),
+    "df3d_hg_forward_argmax": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "df3d_hg_launches_per_forward": (_i, [_vp, _i]),
+}
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m deepfly3d_b200.build` "
+            "(or __graft_entry__.build()).  deepfly3d_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()
+
+
+class Df3dError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.df3d_last_error()
+        raise Df3dError(f"libdf3d_b200 error {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,182 @@
+"""Thin Python wrappers: PyTorch owns device memory and streams, the C ABI does the work.
+
+Every function takes CUDA tensors, enqueues on the current torch stream and returns CUDA tensors
+without synchronising.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("deepfly3d_b200 ops take CUDA tensors (there is no CPU fallback)")
+
+
+def heatmap_argmax(hm):
+    """(B,K,H,W) float32/bfloat16 CUDA -> idx (B,K) int32, conf (B,K) float32."""
+    _need_cuda(hm)
+    if hm.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("heatmap_argmax: dtype must be float32 or bfloat16")
+    hm = hm.contiguous()
+    B, K, H, W = hm.shape
+    idx = torch.empty((B, K), dtype=torch.int32, device=hm.device)
+    conf = torch.empty((B, K), dtype=torch.float32, device=hm.device)
+    check(lib.df3d_heatmap_argmax(_ptr(hm), 0 if hm.dtype == torch.float32 else 1, B, K, H, W,
+                                  _ptr(idx), _ptr(conf), _stream()))
+    return idx, conf
+
+
+def heatmap_argmax_nhwc(hm, K):
+    """(B,H,W,Cpad) float32 CUDA, decode channels [0,K)."""
+    _need_cuda(hm)
+    hm = hm.contiguous()
+    B, H, W, Cp = hm.shape
+    idx = torch.empty((B, K), dtype=torch.int32, device=hm.device)
+    conf = torch.empty((B, K), dtype=torch.float32, device=hm.device)
+    check(lib.df3d_heatmap_argmax_nhwc(_ptr(hm), B, H, W, Cp, K, _ptr(idx), _ptr(conf), _stream()))
+    return idx, conf
+
+
+def pack_points2d(idx, C_, T, heatmap_shape, camera_ordering, image_shape):
+    """idx (C*T,K) int32 (camera-major) -> points2d (C,T,2K,2) f64 normalised (row,col),
+    pts_xy (C,T,2K,2) f64 pixel (x,y).  image_shape = [W, H] like Core.image_shape."""
+    _need_cuda(idx)
+    idx = idx.contiguous()
+    K = idx.shape[1]
+    if idx.shape[0] != C_ * T:
+        raise ValueError("pack_points2d: idx must have C*T rows")
+    Hh, Wh = heatmap_shape
+    order = (C.c_int * C_)(*[int(c) for c in camera_ordering])
+    p2d = torch.empty((C_, T, 2 * K, 2), dtype=torch.float64, device=idx.device)
+    pxy = torch.empty_like(p2d)
+    check(lib.df3d_pack_points2d(_ptr(idx), C_, T, K, Hh, Wh, order, int(image_shape[0]), int(image_shape[1]),
+                                 _ptr(p2d), _ptr(pxy), _stream()))
+    return p2d, pxy
+
+
+def projection_matrices(cam_rt, intr4):
+    """cam_rt (C,6), intr4 (C,4) -> P (C,3,4), R (C,3,3)."""
+    _need_cuda(cam_rt, intr4)
+    Cn = cam_rt.shape[0]
+    P = torch.empty((Cn, 3, 4), dtype=torch.float64, device=cam_rt.device)
+    R = torch.empty((Cn, 3, 3), dtype=torch.float64, device=cam_rt.device)
+    check(lib.df3d_projection_matrices(_ptr(cam_rt.contiguous()), _ptr(intr4.contiguous()), Cn, _ptr(P), _ptr(R), _stream()))
+    return P, R
+
+
+def triangulate_dlt(P, pts_xy):
+    """P (C,3,4) f64, pts_xy (C,T,J,2) f64 pixel (x,y) -> (T,J,3) f64."""
+    _need_cuda(P, pts_xy)
+    if P.dtype != torch.float64 or pts_xy.dtype != torch.float64:
+        raise ValueError("triangulate_dlt: float64 tensors required")
+    P = P.contiguous()
+    pts_xy = pts_xy.contiguous()
+    Cn, T, J, _ = pts_xy.shape
+    out = torch.empty((T, J, 3), dtype=torch.float64, device=pts_xy.device)
+    check(lib.df3d_triangulate_dlt(_ptr(P), _ptr(pts_xy), Cn, T, J, _ptr(out), _stream()))
+    return out
+
+
+def ba_workspace(Cn, T, J, device):
+    n = lib.df3d_bundle_adjust_workspace_bytes(Cn, T, J)
+    return torch.empty(n + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned_ptr(ws):
+    p = ws.data_ptr()
+    a = (p + 255) & ~255
+    return C.c_void_p(a), ws.numel() - (a - p)
+
+
+REPORT_FIELDS = ("cost0", "cost", "lambda", "iters", "accepted", "n_obs", "status")
+
+
+def _decode_report(rep_bytes):
+    raw = rep_bytes.cpu().numpy().tobytes()
+    r = _lib.BAReport.from_buffer_copy(raw)
+    return {"cost0": r.cost0, "cost": r.cost, "lambda": r.lambda_, "iters": r.iters,
+            "accepted": r.accepted, "n_obs": r.n_obs, "status": r.status}
+
+
+def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, lambda0=1e-6, workspace=None):
+    """In-place LM bundle adjustment.  cam_rt (C,6) and pts3d (T,J,3) are updated.
+
+    Returns a uint8 CUDA tensor holding the df3d_ba_report (decode with ``ba_report``; reading it
+    synchronises)."""
+    _need_cuda(cam_rt, intr4, pts_xy, pts3d)
+    for t in (cam_rt, intr4, pts_xy, pts3d):
+        if t.dtype != torch.float64 or not t.is_contiguous():
+            raise ValueError("bundle_adjust: contiguous float64 tensors required")
+    Cn, T, J, _ = pts_xy.shape
+    ws = workspace if workspace is not None else ba_workspace(Cn, T, J, cam_rt.device)
+    wp, wn = _aligned_ptr(ws)
+    opts = _lib.BAOpts(int(max_iters), float(ftol), float(lambda0))
+    rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
+    check(lib.df3d_bundle_adjust(_ptr(cam_rt), _ptr(intr4), _ptr(pts_xy), Cn, T, J, C.byref(opts), _ptr(pts3d),
+                                 _ptr(rep), wp, wn, _stream()))
+    return rep
+
+
+def ba_report(rep):
+    return _decode_report(rep)
+
+
+def bundle_adjust_distributed(cam_rt, intr4, pts_xy, pts3d, group=None, max_iters=20, ftol=1e-4, lambda0=1e-6):
+    """Frame-sharded LM: every rank holds its own frames' observations / points and the replicated
+    cameras; the Schur-reduced camera system and the candidate cost are all-reduced (sum) over
+    `group` each iteration.  Produces the same iterates as the single-GPU solver on the
+    concatenated frames (up to summation order)."""
+    import torch.distributed as dist
+
+    _need_cuda(cam_rt, intr4, pts_xy, pts3d)
+    Cn, T, J, _ = pts_xy.shape
+    ws = ba_workspace(Cn, T, J, cam_rt.device)
+    wp, wn = _aligned_ptr(ws)
+    opts = _lib.BAOpts(int(max_iters), float(ftol), float(lambda0))
+    sysbuf = torch.zeros(lib.df3d_ba_system_doubles(Cn), dtype=torch.float64, device=cam_rt.device)
+    cost = torch.zeros(2, dtype=torch.float64, device=cam_rt.device)
+    rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
+    s = _stream()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    check(lib.df3d_ba_begin(_ptr(cam_rt), C.byref(opts), Cn, T, J, wp, wn, s))
+    for _ in range(max_iters):
+        check(lib.df3d_ba_linearize(_ptr(intr4), _ptr(pts_xy), _ptr(pts3d), Cn, T, J, wp, _ptr(sysbuf), s))
+        if multi:
+            dist.all_reduce(sysbuf, group=group)
+        check(lib.df3d_ba_solve(Cn, wp, _ptr(sysbuf), s))
+        check(lib.df3d_ba_evaluate(_ptr(intr4), _ptr(pts_xy), _ptr(pts3d), Cn, T, J, wp, _ptr(cost), s))
+        if multi:
+            dist.all_reduce(cost, group=group)
+        check(lib.df3d_ba_decide(Cn, T, J, wp, _ptr(cost), _ptr(pts3d), s))
+    check(lib.df3d_ba_end(_ptr(cam_rt), Cn, wp, _ptr(rep), s))
+    return rep
+
+
+def reprojection_error(cam_rt, intr4, pts_xy, pts3d):
+    """Mean L2 pixel error over the used observations, as a 0-d CUDA tensor."""
+    _need_cuda(cam_rt, intr4, pts_xy, pts3d)
+    Cn, T, J, _ = pts_xy.shape
+    out = torch.empty(2, dtype=torch.float64, device=cam_rt.device)
+    check(lib.df3d_reprojection_error(_ptr(cam_rt.contiguous()), _ptr(intr4.contiguous()), _ptr(pts_xy.contiguous()),
+                                      _ptr(pts3d.contiguous()), Cn, T, J, _ptr(out), _stream()))
+    return out[0] / out[1]
+
+
+def intr_to_vec4(intr):
+    """(C,3,3) camera matrices -> (C,4) fx, fy, cx, cy."""
+    intr = np.asarray(intr, dtype=np.float64)
+    return np.stack([intr[:, 0, 0], intr[:, 1, 1], intr[:, 0, 2], intr[:, 1, 2]], axis=1)

@@ -1,0 +1,192 @@
+/*
+ * df3d_b200.h -- C ABI of libdf3d_b200.so, the B200-native (sm_100a) replacement for the
+ * 2D->3D pose hot path of NeLy-EPFL/DeepFly3D.
+ *
+ * The reference has no native/FFI boundary: the seam is the Python surface of the two
+ * un-vendored packages it imports (df3d/core.py:11-12).  Each entry point below names the
+ * reference call site it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_dev` pointer is DEVICE memory owned by the caller
+ *     (PyTorch allocator, cudaMalloc, ...).  The library never allocates or frees on the hot
+ *     path; opaque handles own only their packed weights / launch plans / TMA descriptors.
+ *   - every call is asynchronous w.r.t. the host: work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*), no implicit synchronisation.
+ *   - return value: DF3D_OK (0) or a negative DF3D_E* code; the message of the last failure on
+ *     the calling thread is returned by df3d_last_error().  No exceptions, no exit().
+ *   - one handle must not be used from two streams concurrently; distinct handles are
+ *     independent.  All functions are re-entrant across handles.
+ */
+#ifndef DF3D_B200_H_
+#define DF3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DF3D_ABI_VERSION 1
+
+enum {
+  DF3D_OK = 0,
+  DF3D_EINVAL = -1,     /* bad argument (null pointer, size out of range, misaligned) */
+  DF3D_ECUDA = -2,      /* a CUDA runtime / driver call or kernel launch failed         */
+  DF3D_ENOMEM = -3,     /* caller-provided workspace too small                          */
+  DF3D_EUNSUPPORTED = -4/* shape not supported by the sm_100a kernels                   */
+};
+
+#define DF3D_MAX_CAMS 8   /* reference uses 7 (df3d/config.py:17) */
+
+int df3d_abi_version(void);
+const char* df3d_last_error(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Heat-map decode.  Replaces the per-channel read-out inside df2d.inference.inference_folder
+ * (call site df3d/core.py:177-185; rule documented at README.md:404: argmax_{h,w} H and H[h,w]
+ * as confidence).  First occurrence wins on ties (row-major flat index), like numpy/torch argmax.
+ *
+ *   hm_dev   : (B,K,H,W) contiguous, NCHW.  dtype 0 = float32, 1 = bfloat16
+ *   idx_dev  : (B,K) int32   flat index row*W + col
+ *   conf_dev : (B,K) float32 peak value
+ * ------------------------------------------------------------------------------------------ */
+int df3d_heatmap_argmax(const void* hm_dev, int dtype, int B, int K, int H, int W,
+                        int32_t* idx_dev, float* conf_dev, void* stream);
+
+/* Same decode for the channels-last score tensor the hourglass kernels write:
+ *   hm_dev (B,H,W,Cpad) float32, only channels [0,K) are decoded. */
+int df3d_heatmap_argmax_nhwc(const float* hm_dev, int B, int H, int W, int Cpad, int K,
+                             int32_t* idx_dev, float* conf_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * 19 -> 38 joint packing.  Replaces df3d/core.py:187-203 (Core.pose2d_estimation after
+ * inference_folder) and the pixel scaling of core.py:247 (`points2d * image_shape[::-1]`).
+ *
+ *   idx_dev        : (C*T, K) int32 flat arg-max indices, image b = c*T + t   (camera-major)
+ *   camera_ordering: HOST array of C ints (core.py:65-71)
+ *   points2d_dev   : (C,T,2K,2) float64 normalised (row/Hh, col/Wh) with the reference's
+ *                    blanking and un-flip quirks ((0,1) for unseen joints of cameras 4..6)
+ *   pts_xy_dev     : (C,T,2K,2) float64 pixel (x, y) = (col*img_w, row*img_h); may be NULL
+ * Requires C == 7 (the reference's slicing [:3], [4:], [2], [4] is hard-wired to 7 cameras).
+ * ------------------------------------------------------------------------------------------ */
+int df3d_pack_points2d(const int32_t* idx_dev, int C, int T, int K, int Hh, int Wh,
+                       const int* camera_ordering, int img_w, int img_h,
+                       double* points2d_dev, double* pts_xy_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Multi-view DLT triangulation.  Replaces pyba CameraNetwork.triangulate()
+ * (call site df3d/core.py:355; also used to initialise bundle adjustment).
+ *
+ *   P_dev      : (C,3,4) float64 projection matrices intr @ [R|t]
+ *   pts_xy_dev : (C,T,J,2) float64 pixel (x,y); an observation is used iff x != 0 and y != 0
+ *   pts3d_dev  : (T,J,3) float64; joints seen by < 2 cameras are written as 0
+ * ------------------------------------------------------------------------------------------ */
+int df3d_triangulate_dlt(const double* P_dev, const double* pts_xy_dev, int C, int T, int J,
+                         double* pts3d_dev, void* stream);
+
+/* P = intr @ [R(rvec) | tvec] for C cameras (device helper used between BA and DLT).
+ *   cam_rt_dev (C,6) rvec,tvec ; intr_dev (C,4) fx,fy,cx,cy ; P_dev (C,3,4) ; R_dev (C,3,3) or NULL */
+int df3d_projection_matrices(const double* cam_rt_dev, const double* intr_dev, int C,
+                             double* P_dev, double* R_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Bundle adjustment of the C camera extrinsics + all 3-D points.  Replaces pyba
+ * CameraNetwork.bundle_adjust(update_intrinsic=False, update_distort=False)
+ * (call site df3d/core.py:249).  Levenberg-Marquardt on the Schur-reduced camera system,
+ * column-norm (Jacobi) scaled like SciPy's x_scale='jac', analytic Jacobian, fp64.
+ * Cameras without observations are returned unchanged.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct df3d_ba_opts {
+  int max_iters;      /* LM iterations (accepted + rejected); reference converges in 3-4 */
+  double ftol;        /* stop when dF < ftol * F  (reference: 1e-4)                       */
+  double lambda0;     /* initial damping in the Jacobi-scaled space (default 1e-6)        */
+} df3d_ba_opts;
+
+typedef struct df3d_ba_report {   /* written to DEVICE memory (no host sync) */
+  double cost0;       /* 0.5 * sum r^2 at entry */
+  double cost;        /* at exit                */
+  double lambda;      /* final damping          */
+  int32_t iters;      /* linearisations done    */
+  int32_t accepted;   /* accepted steps         */
+  int32_t n_obs;      /* observations used      */
+  int32_t status;     /* 1 = ftol reached, 0 = max_iters */
+} df3d_ba_report;
+
+size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J);
+
+/*   cam_rt_dev : (C,6) rvec(3),tvec(3) in/out
+ *   intr_dev   : (C,4) fx,fy,cx,cy
+ *   pts_xy_dev : (C,T,J,2) pixel (x,y), visibility rule as in df3d_triangulate_dlt
+ *   pts3d_dev  : (T,J,3) in: initial points (DLT with the initial cameras), out: BA points
+ *   report_dev : df3d_ba_report in device memory (may be NULL)                              */
+int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double* pts_xy_dev,
+                       int C, int T, int J, const df3d_ba_opts* opts, double* pts3d_dev,
+                       df3d_ba_report* report_dev, void* workspace_dev, size_t workspace_bytes,
+                       void* stream);
+
+/* Stepwise form of the same solver for frame-sharded multi-GPU runs: the caller all-reduces
+ * (sum) `sys_dev` (df3d_ba_system_doubles() float64) across ranks between _linearize and
+ * _solve, and `cost_dev` (2 float64: candidate cost, unused) between _evaluate and _decide.
+ * With one rank this is exactly what df3d_bundle_adjust runs internally. */
+size_t df3d_ba_system_doubles(int C);
+int df3d_ba_begin(const double* cam_rt_dev, const df3d_ba_opts* opts, int C, int T, int J,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+int df3d_ba_linearize(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
+                      int C, int T, int J, void* workspace_dev, double* sys_dev, void* stream);
+int df3d_ba_solve(int C, void* workspace_dev, const double* sys_dev, void* stream);
+int df3d_ba_evaluate(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
+                     int C, int T, int J, void* workspace_dev, double* cost_dev, void* stream);
+int df3d_ba_decide(int C, int T, int J, void* workspace_dev, const double* cost_dev,
+                   double* pts3d_dev, void* stream);
+int df3d_ba_end(double* cam_rt_dev, int C, void* workspace_dev, df3d_ba_report* report_dev,
+                void* stream);
+
+/* Mean L2 reprojection error in pixels (pyba CameraNetwork.reprojection_error(), printed at
+ * df3d/core.py:250).  out_dev: 2 float64 = {sum of distances, number of observations}. */
+int df3d_reprojection_error(const double* cam_rt_dev, const double* intr_dev,
+                            const double* pts_xy_dev, const double* pts3d_dev, int C, int T, int J,
+                            double* out_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Stacked-hourglass forward + decode.  Replaces the network forward inside
+ * df2d.inference.inference_folder (call site df3d/core.py:177-185; hyper-parameters hinted at
+ * df3d/config.py:18,33-36).  Convolutions run as tcgen05 implicit-GEMM tiles fed by TMA.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct df3d_hg_desc {
+  int num_stacks;     /* 2 (reference config) or 8 (sh8 weights)          */
+  int num_classes;    /* 19                                               */
+  int in_h, in_w;     /* network input size, multiple of 64 (256x512 ref) */
+  int max_batch;      /* largest B passed to df3d_hg_forward_*            */
+} df3d_hg_desc;
+
+typedef struct df3d_hg df3d_hg;
+
+/* Number of float32 values in the flat parameter blob expected by df3d_hg_create; the layout is
+ * the module order of the oracle model (see deepfly3d_b200/hourglass.py: flatten_params). */
+size_t df3d_hg_param_count(const df3d_hg_desc* desc);
+size_t df3d_hg_workspace_bytes(const df3d_hg_desc* desc);
+
+/* params_host: HOST float32 blob (conv weights OIHW, biases, BN gamma/beta/mean/var).
+ * BN is folded, weights are packed to bf16 K-major tiles and uploaded once. */
+int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host, size_t n_params,
+                   df3d_hg** out);
+void df3d_hg_destroy(df3d_hg* hg);
+
+/*   images_dev : dtype 0: (B,H,W) uint8 gray, replicated to 3 channels, x/255 - mean
+ *                dtype 1: (B,3,H,W) float32 already normalised (what the torch model takes)
+ *   flip_dev   : (B) uint8, 1 = mirror the image left-right before the network
+ *                (camera_ids_to_flip, df3d/core.py:179); may be NULL
+ *   idx_dev    : (B,K) int32, conf_dev : (B,K) float32 (decode of the LAST stack)
+ *   heatmap_dev: optional (B,Hh,Wh,32) float32 copy of the last stack's scores, or NULL      */
+int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int dtype, const uint8_t* flip_dev,
+                           int B, int32_t* idx_dev, float* conf_dev, float* heatmap_dev,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* number of kernels one df3d_hg_forward_argmax call launches (for bench.py's gpu_launches) */
+int df3d_hg_launches_per_forward(const df3d_hg* hg, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DF3D_B200_H_ */
