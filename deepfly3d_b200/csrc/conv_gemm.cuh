@@ -1,0 +1,44 @@
+// Implicit-GEMM convolution (1x1 and 3x3, stride 1, "same" padding) on NHWC bf16 activations for
+// sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma (fp32 accumulators in TMEM) ->
+// tcgen05.ld epilogue with the next layer's BatchNorm/ReLU, the residual add and the bf16
+// rounding fused.  This is the hot loop that replaces the torch conv2d/batch_norm/relu calls of
+// the hourglass inside df2d (reference call site df3d/core.py:177-185).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace df3d {
+
+struct ConvParams {
+  CUtensorMap tmA;  // activations, 4-D (C, W, H, N), box (64, tw, th, nb), SWIZZLE_128B, OOB = 0
+  CUtensorMap tmB;  // weights, 2-D (K, CoutPad) K-major, box (64, BN), SWIZZLE_128B
+  int taps;         // 1 (1x1) or 9 (3x3)
+  int kc_per_tap;   // CinPad / 64
+  int H, W, B;      // spatial size and number of images of this launch
+  int tw, th, nb;   // M tile = nb images x th rows x tw cols = 128 pixels
+  int tiles_x, tiles_y, tiles_b;
+  int n_tiles_n;    // CoutPad / BN
+  // epilogue:  v = acc*scale1[c] + shift1[c] (+ residual) ; relu1 ; out_raw = bf16(v) ;
+  //            out_f32 = v ; out_act = bf16(relu(bf16(v)*scale2[c] + shift2[c]))
+  const float* scale1;
+  const float* shift1;
+  const float* scale2;
+  const float* shift2;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out_raw;
+  __nv_bfloat16* out_act;
+  float* out_f32;
+  int res_ld, raw_ld, act_ld, f32_ld;  // channel strides (elements per pixel)
+  int relu1;
+};
+
+// host side ------------------------------------------------------------------------------------
+int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no libcuda link dependency)
+int make_tmap_act(CUtensorMap* out, const void* base, int C, int W, int H, int N, int tw, int th, int nb);
+int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int CoutPad, int BN);
+int launch_conv_gemm(const ConvParams& p, int BN, int num_sms, cudaStream_t stream);
+int conv_gemm_configure();  // cudaFuncSetAttribute for the dynamic shared memory of every instantiation
+
+}  // namespace df3d

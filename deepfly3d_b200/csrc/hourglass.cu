@@ -1,0 +1,766 @@
+// Stacked-hourglass forward as a static plan of sm_100a kernels (host-side executor + C ABI).
+// Replaces the network forward + decode inside df2d.inference.inference_folder (reference call
+// site df3d/core.py:177-185).
+//
+// df3d_hg_create parses the float32 parameter blob, folds every BatchNorm into a per-channel
+// (scale, shift) pair, packs every conv weight to bf16 [CoutPad][taps*CinPad] (K-major) and
+// uploads both once.  The forward is a fixed list of launches over a chunk of images:
+//   stem_im2col -> conv_gemm (tcgen05) x N, maxpool_bn_relu, upsample_add_bn_relu -> argmax.
+// Each conv's epilogue applies the *next* BatchNorm + ReLU (pre-activation bottlenecks), the
+// residual add and the bf16 rounding, so a bottleneck is exactly three (four with a projection)
+// GEMM launches and no elementwise pass.  All activations live in the caller's workspace; a
+// small free-list arena reuses buffers so the working set stays small.
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "hg_elementwise.cuh"
+
+namespace df3d {
+
+constexpr float kBnEps = 1e-5f;
+constexpr int kDepth = 4;
+constexpr int kFeats = 128;        // bottleneck planes inside the hourglass
+constexpr int kCh = 2 * kFeats;    // 256 channels on the residual stream
+constexpr int kInplanes = 64;
+constexpr int kHeatPad = 32;       // fp32 score channels stored per pixel (>= num_classes)
+
+static inline uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// ------------------------------------------------------------------------------ parameter views
+struct BNp {
+  const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
+  int n = 0;
+};
+struct Convp {
+  const float *w = nullptr, *bias = nullptr;
+  int cout = 0, cin = 0, k = 0;
+};
+struct Bott {
+  BNp bn1, bn2, bn3;
+  Convp c1, c2, c3, ds;
+  bool has_ds = false;
+  int inpl = 0, planes = 0;
+};
+struct StackP {
+  Bott hg[kDepth][4];  // hg[d][0..2], hg[0][3]
+  Bott res;
+  Convp fc;
+  BNp fc_bn;
+  Convp score, fc_, score_;
+};
+struct NetP {
+  Convp conv1;
+  BNp bn1;
+  Bott layer1, layer2, layer3;
+  std::vector<StackP> stacks;
+};
+
+struct Cursor {
+  const float* p;
+  size_t n, pos = 0;
+  bool ok = true;
+  const float* take(size_t k) {
+    if (pos + k > n) {
+      ok = false;
+      return p;  // caller checks ok
+    }
+    const float* r = p + pos;
+    pos += k;
+    return r;
+  }
+};
+
+static BNp read_bn(Cursor& c, int n) {
+  BNp b;
+  b.n = n;
+  b.g = c.take(n);
+  b.b = c.take(n);
+  b.m = c.take(n);
+  b.v = c.take(n);
+  return b;
+}
+static Convp read_conv(Cursor& c, int cout, int cin, int k) {
+  Convp v;
+  v.cout = cout;
+  v.cin = cin;
+  v.k = k;
+  v.w = c.take((size_t)cout * cin * k * k);
+  v.bias = c.take(cout);
+  return v;
+}
+static Bott read_bott(Cursor& c, int inpl, int planes) {
+  Bott b;
+  b.inpl = inpl;
+  b.planes = planes;
+  b.bn1 = read_bn(c, inpl);
+  b.c1 = read_conv(c, planes, inpl, 1);
+  b.bn2 = read_bn(c, planes);
+  b.c2 = read_conv(c, planes, planes, 3);
+  b.bn3 = read_bn(c, planes);
+  b.c3 = read_conv(c, 2 * planes, planes, 1);
+  b.has_ds = inpl != 2 * planes;
+  if (b.has_ds) b.ds = read_conv(c, 2 * planes, inpl, 1);
+  return b;
+}
+static void read_net(Cursor& c, int num_stacks, int K, NetP* net) {
+  net->conv1 = read_conv(c, kInplanes, 3, 7);
+  net->bn1 = read_bn(c, kInplanes);
+  net->layer1 = read_bott(c, kInplanes, kInplanes);
+  net->layer2 = read_bott(c, 2 * kInplanes, kInplanes);
+  net->layer3 = read_bott(c, 2 * kInplanes, kFeats);
+  net->stacks.resize(num_stacks);
+  for (int i = 0; i < num_stacks; ++i) {
+    StackP& s = net->stacks[i];
+    for (int d = 0; d < kDepth; ++d)
+      for (int k = 0; k < (d == 0 ? 4 : 3); ++k) s.hg[d][k] = read_bott(c, kCh, kFeats);
+    s.res = read_bott(c, kCh, kFeats);
+    s.fc = read_conv(c, kCh, kCh, 1);
+    s.fc_bn = read_bn(c, kCh);
+    s.score = read_conv(c, K, kCh, 1);
+    if (i < num_stacks - 1) {
+      s.fc_ = read_conv(c, kCh, kCh, 1);
+      s.score_ = read_conv(c, kCh, K, 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ plan
+struct Tensor {
+  size_t off = 0;  // byte offset in the workspace
+  size_t bytes = 0;
+  int H = 0, W = 0, C = 0;
+  bool valid = false;
+};
+
+struct Arena {
+  size_t top = 0;
+  std::multimap<size_t, size_t> free_blocks;  // bytes -> offset
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    auto it = free_blocks.find(bytes);
+    if (it != free_blocks.end()) {
+      size_t o = it->second;
+      free_blocks.erase(it);
+      return o;
+    }
+    size_t o = top;
+    top += bytes;
+    return o;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    free_blocks.emplace(bytes, off);
+  }
+};
+
+enum OpKind { OP_IM2COL, OP_CONV, OP_POOL, OP_UPADD, OP_ARGMAX };
+
+struct Op {
+  OpKind kind;
+  // conv
+  ConvParams conv;
+  int BN = 0, nb = 1;
+  // elementwise / argmax: byte offsets resolved to pointers at plan time
+  char *in0 = nullptr, *in1 = nullptr, *out0 = nullptr, *out1 = nullptr;
+  const float *scale = nullptr, *shift = nullptr;
+  int H = 0, W = 0, C = 0;
+};
+
+struct Affine {  // index into the float blob
+  size_t scale_off, shift_off;
+};
+
+}  // namespace df3d
+
+using namespace df3d;
+
+struct df3d_hg {
+  df3d_hg_desc desc;
+  float mean[3] = {0.5f, 0.5f, 0.5f};
+  int chunk = 0;
+  int num_sms = 148;
+  std::vector<float> params;  // host copy of the blob (views in `net` point into it)
+  NetP net;
+  // host-side packed data (filled during the sizing pass)
+  std::vector<uint16_t> wblob;
+  std::vector<float> ablob;
+  uint16_t* d_w = nullptr;
+  float* d_a = nullptr;
+  size_t ws_bytes = 0;
+  int ops_per_chunk = 0;
+  // plan for the workspace pointer it was built for
+  char* plan_base = nullptr;
+  std::vector<Op> ops;
+  char* heat_ptr = nullptr;  // fp32 score tensor of the last stack inside the workspace
+  int Hh = 0, Wh = 0;
+};
+
+namespace df3d {
+
+// One emission pass.  dry == true: pack weights / affines on the host and size the workspace.
+// dry == false: same traversal (identical offsets), but produce launchable ops for `base`.
+struct Emitter {
+  df3d_hg* hg;
+  bool dry;
+  char* base;
+  Arena arena;
+  size_t w_cursor = 0, a_cursor = 0;
+  int err = DF3D_OK;
+  int B;  // chunk
+  int n_ops = 0;  // launches per chunk (counted in both passes)
+
+  Tensor talloc(int H, int W, int C, int elem = 2) {
+    Tensor t;
+    t.H = H;
+    t.W = W;
+    t.C = C;
+    t.bytes = (size_t)B * H * W * C * elem;
+    t.off = arena.alloc(t.bytes);
+    t.valid = true;
+    return t;
+  }
+  void tfree(Tensor& t) {
+    if (t.valid) arena.release(t.off, t.bytes);
+    t.valid = false;
+  }
+  char* ptr(const Tensor& t) const { return t.valid ? base + t.off : nullptr; }
+
+  // reserve n floats in the affine blob; returns offset
+  size_t areserve(size_t n) {
+    size_t o = a_cursor;
+    a_cursor += n;
+    if (dry && hg->ablob.size() < a_cursor) hg->ablob.resize(a_cursor, 0.0f);
+    return o;
+  }
+  // folded BN: y = x*scale + shift
+  Affine bn_affine(const BNp& bn, int pad) {
+    Affine a{areserve(pad), areserve(pad)};
+    if (dry) {
+      for (int i = 0; i < bn.n; ++i) {
+        const float s = bn.g[i] / std::sqrt(bn.v[i] + kBnEps);
+        hg->ablob[a.scale_off + i] = s;
+        hg->ablob[a.shift_off + i] = bn.b[i] - bn.m[i] * s;
+      }
+    }
+    return a;
+  }
+  // conv epilogue affine: v = acc*scale + shift where the conv has `bias` and is optionally
+  // followed by BN `bn`:  (acc + bias)*s + t
+  Affine conv_affine(const Convp& c, const BNp* bn, int pad) {
+    Affine a{areserve(pad), areserve(pad)};
+    if (dry) {
+      for (int i = 0; i < pad; ++i) {
+        float s = 1.0f, t = 0.0f, b = i < c.cout ? c.bias[i] : 0.0f;
+        if (bn && i < bn->n) {
+          s = bn->g[i] / std::sqrt(bn->v[i] + kBnEps);
+          t = bn->b[i] - bn->m[i] * s;
+        }
+        if (i >= c.cout) s = 0.0f;
+        hg->ablob[a.scale_off + i] = s;
+        hg->ablob[a.shift_off + i] = b * s + t;
+      }
+    }
+    return a;
+  }
+  // pack OIHW fp32 -> bf16 [CoutPad][taps*CinPad], K index = tap*CinPad + cin
+  size_t pack_weights(const Convp& c, int CoutPad, int CinPad) {
+    const int taps = c.k * c.k;
+    const size_t K = (size_t)taps * CinPad;
+    size_t o = w_cursor;
+    w_cursor += (size_t)CoutPad * K;
+    if (dry) {
+      hg->wblob.resize(w_cursor, 0);
+      for (int co = 0; co < c.cout; ++co)
+        for (int ci = 0; ci < c.cin; ++ci)
+          for (int t = 0; t < taps; ++t)
+            hg->wblob[o + (size_t)co * K + (size_t)t * CinPad + ci] = f2bf(c.w[((size_t)co * c.cin + ci) * taps + t]);
+    }
+    return o;
+  }
+  // stem: K index = (ky*7+kx)*3 + c  (must match stem_im2col_kernel), padded to 192
+  size_t pack_stem(const Convp& c) {
+    const size_t K = kStemKPadCols;
+    size_t o = w_cursor;
+    w_cursor += (size_t)c.cout * K;
+    if (dry) {
+      hg->wblob.resize(w_cursor, 0);
+      for (int co = 0; co < c.cout; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 49; ++t)
+            hg->wblob[o + (size_t)co * K + (size_t)t * 3 + ci] = f2bf(c.w[((size_t)co * 3 + ci) * 49 + t]);
+    }
+    return o;
+  }
+
+  static void tile_geometry(int H, int W, int* tw, int* th, int* nb) {
+    int w = W < 16 ? W : 16;
+    int h = 128 / w;
+    if (h > H) h = H;
+    *tw = w;
+    *th = h;
+    *nb = 128 / (w * h);
+  }
+
+  // Generic conv emission.  `in` is the A operand (already activated), weights at w_off with
+  // K = taps*CinPad.  Outputs may be invalid tensors (skipped).
+  void conv(const Tensor& in, size_t w_off, int taps, int CinPad, int CoutPad, int BN, Affine a1, bool relu1,
+            const Tensor* residual, const Tensor* out_raw, const Affine* a2, const Tensor* out_act,
+            const Tensor* out_f32) {
+    ++n_ops;
+    if (err) return;
+    if (dry) return;
+    Op op;
+    op.kind = OP_CONV;
+    op.BN = BN;
+    ConvParams& p = op.conv;
+    memset(&p, 0, sizeof(p));
+    int tw, th, nb;
+    tile_geometry(in.H, in.W, &tw, &th, &nb);
+    op.nb = nb;
+    if ((err = make_tmap_act(&p.tmA, ptr(in), in.C, in.W, in.H, B, tw, th, nb))) return;
+    if ((err = make_tmap_wgt(&p.tmB, hg->d_w + w_off, taps * CinPad, CoutPad, BN))) return;
+    p.taps = taps;
+    p.kc_per_tap = CinPad / 64;
+    p.H = in.H;
+    p.W = in.W;
+    p.B = B;
+    p.tw = tw;
+    p.th = th;
+    p.nb = nb;
+    p.tiles_x = in.W / tw;
+    p.tiles_y = in.H / th;
+    p.tiles_b = (B + nb - 1) / nb;
+    p.n_tiles_n = CoutPad / BN;
+    p.scale1 = hg->d_a + a1.scale_off;
+    p.shift1 = hg->d_a + a1.shift_off;
+    p.relu1 = relu1 ? 1 : 0;
+    if (residual && residual->valid) {
+      p.residual = reinterpret_cast<const __nv_bfloat16*>(ptr(*residual));
+      p.res_ld = residual->C;
+    }
+    if (out_raw && out_raw->valid) {
+      p.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*out_raw));
+      p.raw_ld = out_raw->C;
+    }
+    if (out_act && out_act->valid && a2) {
+      p.out_act = reinterpret_cast<__nv_bfloat16*>(ptr(*out_act));
+      p.act_ld = out_act->C;
+      p.scale2 = hg->d_a + a2->scale_off;
+      p.shift2 = hg->d_a + a2->shift_off;
+    }
+    if (out_f32 && out_f32->valid) {
+      p.out_f32 = reinterpret_cast<float*>(ptr(*out_f32));
+      p.f32_ld = out_f32->C;
+    }
+    hg->ops.push_back(op);
+  }
+
+  static int bn_for(int cout_pad) { return cout_pad >= 256 ? 256 : cout_pad; }
+
+  // pre-activation bottleneck: x (raw) / xa = relu(bn1(x)) -> y (raw) [+ ya = relu(next_bn(y))]
+  void bottleneck(const Bott& b, const Tensor& x, const Tensor& xa, const BNp* next_bn, Tensor* y, Tensor* ya) {
+    const int H = x.H, W = x.W, P = b.planes, O = 2 * b.planes;
+    // conv1 (1x1) with bn2+relu folded into its epilogue
+    size_t w1 = pack_weights(b.c1, P, b.inpl);
+    Affine a1 = conv_affine(b.c1, &b.bn2, P);
+    Tensor t1 = talloc(H, W, P);
+    conv(xa, w1, 1, b.inpl, P, bn_for(P), a1, true, nullptr, &t1, nullptr, nullptr, nullptr);
+    // conv2 (3x3) with bn3+relu folded
+    size_t w2 = pack_weights(b.c2, P, P);
+    Affine a2 = conv_affine(b.c2, &b.bn3, P);
+    Tensor t2 = talloc(H, W, P);
+    conv(t1, w2, 9, P, P, bn_for(P), a2, true, nullptr, &t2, nullptr, nullptr, nullptr);
+    tfree(t1);
+    // projection shortcut on the raw input
+    Tensor d;
+    const Tensor* res = &x;
+    if (b.has_ds) {
+      size_t wd = pack_weights(b.ds, O, b.inpl);
+      Affine ad = conv_affine(b.ds, nullptr, O);
+      d = talloc(H, W, O);
+      conv(x, wd, 1, b.inpl, O, bn_for(O), ad, false, nullptr, &d, nullptr, nullptr, nullptr);
+      res = &d;
+    }
+    // conv3 (1x1) + residual, optionally emitting the next block's activated input
+    size_t w3 = pack_weights(b.c3, O, P);
+    Affine a3 = conv_affine(b.c3, nullptr, O);
+    *y = talloc(H, W, O);
+    Affine an{};
+    if (next_bn) {
+      an = bn_affine(*next_bn, O);
+      *ya = talloc(H, W, O);
+    } else {
+      *ya = Tensor();
+    }
+    conv(t2, w3, 1, P, O, bn_for(O), a3, false, res, y, next_bn ? &an : nullptr, ya, nullptr);
+    tfree(t2);
+    tfree(d);
+  }
+
+  void pool(const Tensor& x, const BNp& bn, Tensor* p, Tensor* pa) {
+    Affine a = bn_affine(bn, x.C);
+    *p = talloc(x.H / 2, x.W / 2, x.C);
+    *pa = talloc(x.H / 2, x.W / 2, x.C);
+    ++n_ops;
+    if (dry || err) return;
+    Op op;
+    op.kind = OP_POOL;
+    op.in0 = ptr(x);
+    op.out0 = ptr(*p);
+    op.out1 = ptr(*pa);
+    op.scale = hg->d_a + a.scale_off;
+    op.shift = hg->d_a + a.shift_off;
+    op.H = x.H;
+    op.W = x.W;
+    op.C = x.C;
+    hg->ops.push_back(op);
+  }
+
+  void upadd(const Tensor& up1, const Tensor& low, const BNp& bn, Tensor* o, Tensor* oa) {
+    Affine a = bn_affine(bn, up1.C);
+    *o = talloc(up1.H, up1.W, up1.C);
+    *oa = talloc(up1.H, up1.W, up1.C);
+    ++n_ops;
+    if (dry || err) return;
+    Op op;
+    op.kind = OP_UPADD;
+    op.in0 = ptr(up1);
+    op.in1 = ptr(low);
+    op.out0 = ptr(*o);
+    op.out1 = ptr(*oa);
+    op.scale = hg->d_a + a.scale_off;
+    op.shift = hg->d_a + a.shift_off;
+    op.H = up1.H;
+    op.W = up1.W;
+    op.C = up1.C;
+    hg->ops.push_back(op);
+  }
+
+  // level n of the recursive hourglass of stack s; x/xa stay owned by the caller
+  void hourglass(const StackP& s, int n, const Tensor& x, const Tensor& xa, const BNp& out_bn, Tensor* o, Tensor* oa) {
+    Tensor up1, none;
+    bottleneck(s.hg[n - 1][0], x, xa, nullptr, &up1, &none);
+    Tensor p, pa;
+    pool(x, s.hg[n - 1][1].bn1, &p, &pa);
+    Tensor l1, l1a;
+    const BNp& low1_next = (n > 1) ? s.hg[n - 2][0].bn1 : s.hg[0][3].bn1;
+    bottleneck(s.hg[n - 1][1], p, pa, &low1_next, &l1, &l1a);
+    tfree(p);
+    tfree(pa);
+    Tensor l2, l2a;
+    if (n > 1)
+      hourglass(s, n - 1, l1, l1a, s.hg[n - 1][2].bn1, &l2, &l2a);
+    else
+      bottleneck(s.hg[0][3], l1, l1a, &s.hg[0][2].bn1, &l2, &l2a);
+    tfree(l1);
+    tfree(l1a);
+    Tensor l3;
+    bottleneck(s.hg[n - 1][2], l2, l2a, nullptr, &l3, &none);
+    tfree(l2);
+    tfree(l2a);
+    upadd(up1, l3, out_bn, o, oa);
+    tfree(up1);
+    tfree(l3);
+  }
+
+  void run() {
+    const df3d_hg_desc& d = hg->desc;
+    const NetP& net = hg->net;
+    const int K = d.num_classes;
+    const int H2 = d.in_h / 2, W2 = d.in_w / 2, H4 = d.in_h / 4, W4 = d.in_w / 4;
+    hg->Hh = H4;
+    hg->Wh = W4;
+
+    // ---- stem: im2col + GEMM with bn1+relu folded; also emits layer1's activated input
+    Tensor col = talloc(H2, W2, kStemKPadCols);
+    n_ops += 2;  // im2col + argmax
+    if (!dry && !err) {
+      Op op;
+      op.kind = OP_IM2COL;
+      op.out0 = ptr(col);
+      hg->ops.push_back(op);
+    }
+    size_t w0 = pack_stem(net.conv1);
+    Affine a0 = conv_affine(net.conv1, &net.bn1, kInplanes);
+    Affine a0n = bn_affine(net.layer1.bn1, kInplanes);
+    Tensor x = talloc(H2, W2, kInplanes), xa = talloc(H2, W2, kInplanes);
+    conv(col, w0, 1, kStemKPadCols, kInplanes, 64, a0, true, nullptr, &x, &a0n, &xa, nullptr);
+    tfree(col);
+
+    Tensor y1, none;
+    bottleneck(net.layer1, x, xa, nullptr, &y1, &none);
+    tfree(x);
+    tfree(xa);
+    Tensor p, pa;
+    pool(y1, net.layer2.bn1, &p, &pa);
+    tfree(y1);
+    Tensor y2, y2a;
+    bottleneck(net.layer2, p, pa, &net.layer3.bn1, &y2, &y2a);
+    tfree(p);
+    tfree(pa);
+    Tensor x0, x0a;
+    bottleneck(net.layer3, y2, y2a, &net.stacks[0].hg[kDepth - 1][0].bn1, &x0, &x0a);
+    tfree(y2);
+    tfree(y2a);
+
+    const int S = d.num_stacks;
+    for (int i = 0; i < S; ++i) {
+      const StackP& s = net.stacks[i];
+      Tensor h, ha;
+      hourglass(s, kDepth, x0, x0a, s.res.bn1, &h, &ha);
+      Tensor r;
+      bottleneck(s.res, h, ha, nullptr, &r, &none);
+      tfree(h);
+      tfree(ha);
+      // fc: conv -> BN -> ReLU (post-activation), input is the raw residual stream
+      size_t wf = pack_weights(s.fc, kCh, kCh);
+      Affine af = conv_affine(s.fc, &s.fc_bn, kCh);
+      Tensor f = talloc(H4, W4, kCh);
+      conv(r, wf, 1, kCh, kCh, 256, af, true, nullptr, &f, nullptr, nullptr, nullptr);
+      tfree(r);
+      if (i == S - 1) {
+        size_t wsc = pack_weights(s.score, kHeatPad, kCh);
+        Affine as = conv_affine(s.score, nullptr, kHeatPad);
+        Tensor heat = talloc(H4, W4, kHeatPad, 4);
+        conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat);
+        tfree(f);
+        if (!dry && !err) {
+          Op op;
+          op.kind = OP_ARGMAX;
+          op.in0 = ptr(heat);
+          op.H = H4;
+          op.W = W4;
+          op.C = kHeatPad;
+          hg->ops.push_back(op);
+          hg->heat_ptr = ptr(heat);
+        }
+        tfree(heat);
+        tfree(x0);
+        tfree(x0a);
+      } else {
+        // intermediate score, kept as bf16 with 64 channels (rows >= K of the weights are zero)
+        size_t wsc = pack_weights(s.score, 64, kCh);
+        Affine as = conv_affine(s.score, nullptr, 64);
+        Tensor sc = talloc(H4, W4, 64);
+        conv(f, wsc, 1, kCh, 64, 64, as, false, nullptr, &sc, nullptr, nullptr, nullptr);
+        // u = fc_(f) + x
+        size_t wf_ = pack_weights(s.fc_, kCh, kCh);
+        Affine af_ = conv_affine(s.fc_, nullptr, kCh);
+        Tensor u = talloc(H4, W4, kCh);
+        conv(f, wf_, 1, kCh, kCh, 256, af_, false, &x0, &u, nullptr, nullptr, nullptr);
+        tfree(f);
+        tfree(x0);
+        tfree(x0a);
+        // x' = score_(score) + u, and its activated copy for the next stack's first bottleneck
+        size_t ws_ = pack_weights(s.score_, kCh, 64);
+        Affine as_ = conv_affine(s.score_, nullptr, kCh);
+        Affine an = bn_affine(net.stacks[i + 1].hg[kDepth - 1][0].bn1, kCh);
+        x0 = talloc(H4, W4, kCh);
+        x0a = talloc(H4, W4, kCh);
+        conv(sc, ws_, 1, 64, kCh, 256, as_, false, &u, &x0, &an, &x0a, nullptr);
+        tfree(u);
+        tfree(sc);
+      }
+    }
+    (void)K;
+  }
+};
+
+static size_t param_count(const df3d_hg_desc& d) {
+  static const float dummy = 0.0f;  // count by walking the reader; the views are never dereferenced
+  Cursor c{&dummy, (size_t)-1};
+  NetP net;
+  read_net(c, d.num_stacks, d.num_classes, &net);
+  return c.pos;
+}
+
+static int check_desc(const df3d_hg_desc* d, const char* fn) {
+  DF3D_REQUIRE(d, DF3D_EINVAL, "%s: null desc", fn);
+  DF3D_REQUIRE(d->num_stacks >= 1 && d->num_stacks <= 16, DF3D_EINVAL, "%s: num_stacks must be in [1,16]", fn);
+  DF3D_REQUIRE(d->num_classes >= 1 && d->num_classes <= kHeatPad, DF3D_EINVAL, "%s: num_classes must be in [1,%d]", fn, kHeatPad);
+  DF3D_REQUIRE(d->in_h >= 64 && d->in_w >= 64 && d->in_h % 64 == 0 && d->in_w % 64 == 0 && d->in_h <= 4096 && d->in_w <= 4096,
+               DF3D_EINVAL, "%s: input size must be a multiple of 64 in [64,4096]", fn);
+  DF3D_REQUIRE(d->max_batch >= 1, DF3D_EINVAL, "%s: max_batch must be >= 1", fn);
+  return DF3D_OK;
+}
+
+}  // namespace df3d
+
+extern "C" size_t df3d_hg_param_count(const df3d_hg_desc* desc) {
+  if (check_desc(desc, "df3d_hg_param_count")) return 0;
+  return param_count(*desc);
+}
+
+static int chunk_for(const df3d_hg_desc& d) {
+  // images per launch sequence: enough tiles to fill 148 SMs on the coarse levels, small enough
+  // that the activations of one layer stay L2-friendly
+  long long px = (long long)d.in_h * d.in_w;
+  int c = (int)((128ll * 256 * 256) / px);
+  if (c < 8) c = 8;
+  if (c > d.max_batch) c = d.max_batch;
+  return c;
+}
+
+extern "C" size_t df3d_hg_workspace_bytes(const df3d_hg_desc* desc) {
+  if (check_desc(desc, "df3d_hg_workspace_bytes")) return 0;
+  df3d_hg tmp;
+  tmp.desc = *desc;
+  tmp.chunk = chunk_for(*desc);
+  tmp.params.assign(param_count(*desc), 0.0f);
+  Cursor c{tmp.params.data(), tmp.params.size()};
+  read_net(c, desc->num_stacks, desc->num_classes, &tmp.net);
+  Emitter e{&tmp, true, nullptr};
+  e.B = tmp.chunk;
+  e.run();
+  return e.arena.top + 1024;
+}
+
+extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host, size_t n_params, df3d_hg** out) {
+  if (int e = check_desc(desc, "df3d_hg_create")) return e;
+  DF3D_REQUIRE(params_host && out, DF3D_EINVAL, "df3d_hg_create: null pointer");
+  const size_t need = param_count(*desc);
+  DF3D_REQUIRE(n_params == need, DF3D_EINVAL, "df3d_hg_create: expected %zu parameters, got %zu", need, n_params);
+  int dev = 0;
+  DF3D_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DF3D_CUDA(cudaGetDeviceProperties(&prop, dev));
+  DF3D_REQUIRE(prop.major == 10, DF3D_EUNSUPPORTED, "df3d_hg_create: needs an sm_100 GPU (found sm_%d%d); there is no fallback path",
+               prop.major, prop.minor);
+  if (int e = tma_init()) return e;
+  if (int e = conv_gemm_configure()) return e;
+
+  df3d_hg* hg = new df3d_hg();
+  hg->desc = *desc;
+  hg->num_sms = prop.multiProcessorCount;
+  hg->chunk = chunk_for(*desc);
+  hg->params.assign(params_host, params_host + n_params);
+  Cursor c{hg->params.data(), hg->params.size()};
+  read_net(c, desc->num_stacks, desc->num_classes, &hg->net);
+  if (!c.ok || c.pos != n_params) {
+    delete hg;
+    DF3D_REQUIRE(false, DF3D_EINVAL, "df3d_hg_create: parameter blob does not match the architecture");
+  }
+  Emitter e{hg, true, nullptr};
+  e.B = hg->chunk;
+  e.run();
+  hg->ws_bytes = e.arena.top + 1024;
+  hg->ops_per_chunk = e.n_ops;
+  cudaError_t ce = cudaMalloc(&hg->d_w, hg->wblob.size() * sizeof(uint16_t));
+  if (ce == cudaSuccess) ce = cudaMalloc(&hg->d_a, hg->ablob.size() * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_w, hg->wblob.data(), hg->wblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_a, hg->ablob.data(), hg->ablob.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    set_error("df3d_hg_create: uploading packed weights failed: %s", cudaGetErrorString(ce));
+    (void)cudaGetLastError();
+    if (hg->d_w) cudaFree(hg->d_w);
+    if (hg->d_a) cudaFree(hg->d_a);
+    delete hg;
+    return DF3D_ECUDA;
+  }
+  std::vector<uint16_t>().swap(hg->wblob);  // host copies no longer needed
+  *out = hg;
+  return DF3D_OK;
+}
+
+extern "C" void df3d_hg_destroy(df3d_hg* hg) {
+  if (!hg) return;
+  if (hg->d_w) cudaFree(hg->d_w);
+  if (hg->d_a) cudaFree(hg->d_a);
+  delete hg;
+}
+
+static int build_plan(df3d_hg* hg, char* base) {
+  hg->ops.clear();
+  hg->heat_ptr = nullptr;
+  Emitter e{hg, false, base};
+  e.B = hg->chunk;
+  e.run();
+  if (e.err) return e.err;
+  hg->plan_base = base;
+  return DF3D_OK;
+}
+
+extern "C" int df3d_hg_launches_per_forward(const df3d_hg* hg, int B) {
+  if (!hg || B <= 0) return 0;
+  const int chunks = (B + hg->chunk - 1) / hg->chunk;
+  return hg->ops_per_chunk * chunks;
+}
+
+extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int dtype, const uint8_t* flip_dev,
+                                      int B, int32_t* idx_dev, float* conf_dev, float* heatmap_dev,
+                                      void* workspace_dev, size_t workspace_bytes, void* stream) {
+  DF3D_REQUIRE(hg && images_dev && idx_dev && conf_dev && workspace_dev, DF3D_EINVAL, "df3d_hg_forward_argmax: null pointer");
+  DF3D_REQUIRE(dtype == 0 || dtype == 1, DF3D_EINVAL, "df3d_hg_forward_argmax: dtype must be 0 (uint8 gray) or 1 (float32 NCHW)");
+  DF3D_REQUIRE(B >= 0 && B <= hg->desc.max_batch, DF3D_EINVAL, "df3d_hg_forward_argmax: B=%d exceeds max_batch=%d", B, hg->desc.max_batch);
+  DF3D_REQUIRE(workspace_bytes >= hg->ws_bytes, DF3D_ENOMEM, "df3d_hg_forward_argmax: workspace too small (%zu < %zu bytes)",
+               workspace_bytes, hg->ws_bytes);
+  if (B == 0) return DF3D_OK;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace_dev) + 1023) & ~uintptr_t(1023));
+  if (hg->plan_base != base || hg->ops.empty())
+    if (int e = build_plan(hg, base)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const df3d_hg_desc& d = hg->desc;
+  const int K = d.num_classes;
+  const size_t img_stride = dtype == 0 ? (size_t)d.in_h * d.in_w : (size_t)3 * d.in_h * d.in_w * sizeof(float);
+  const size_t heat_elems = (size_t)hg->Hh * hg->Wh * kHeatPad;
+
+  for (int c0 = 0; c0 < B; c0 += hg->chunk) {
+    const int bc = (B - c0) < hg->chunk ? (B - c0) : hg->chunk;
+    for (const Op& op : hg->ops) {
+      switch (op.kind) {
+        case OP_IM2COL: {
+          const char* img = static_cast<const char*>(images_dev) + (size_t)c0 * img_stride;
+          if (int e = launch_stem_im2col(img, dtype, flip_dev ? flip_dev + c0 : nullptr, bc, d.in_h, d.in_w, hg->mean,
+                                         reinterpret_cast<__nv_bfloat16*>(op.out0), s))
+            return e;
+          break;
+        }
+        case OP_CONV: {
+          ConvParams p = op.conv;
+          p.B = bc;
+          p.tiles_b = (bc + op.nb - 1) / op.nb;
+          if (int e = launch_conv_gemm(p, op.BN, hg->num_sms, s)) return e;
+          break;
+        }
+        case OP_POOL:
+          if (int e = launch_maxpool_bn_relu(reinterpret_cast<const __nv_bfloat16*>(op.in0), bc, op.H, op.W, op.C, op.scale,
+                                             op.shift, reinterpret_cast<__nv_bfloat16*>(op.out0),
+                                             reinterpret_cast<__nv_bfloat16*>(op.out1), s))
+            return e;
+          break;
+        case OP_UPADD:
+          if (int e = launch_upsample_add_bn_relu(reinterpret_cast<const __nv_bfloat16*>(op.in0),
+                                                  reinterpret_cast<const __nv_bfloat16*>(op.in1), bc, op.H, op.W, op.C,
+                                                  op.scale, op.shift, reinterpret_cast<__nv_bfloat16*>(op.out0),
+                                                  reinterpret_cast<__nv_bfloat16*>(op.out1), s))
+            return e;
+          break;
+        case OP_ARGMAX:
+          if (int e = df3d_heatmap_argmax_nhwc(reinterpret_cast<const float*>(op.in0), bc, op.H, op.W, op.C, K,
+                                               idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, stream))
+            return e;
+          if (heatmap_dev)
+            DF3D_CUDA(cudaMemcpyAsync(heatmap_dev + (size_t)c0 * heat_elems, op.in0, (size_t)bc * heat_elems * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+          break;
+      }
+    }
+  }
+  return DF3D_OK;
+}
+
+extern "C" int df3d_hg_set_mean(df3d_hg* hg, float m0, float m1, float m2) {
+  DF3D_REQUIRE(hg, DF3D_EINVAL, "df3d_hg_set_mean: null handle");
+  hg->mean[0] = m0;
+  hg->mean[1] = m1;
+  hg->mean[2] = m2;
+  return DF3D_OK;
+}

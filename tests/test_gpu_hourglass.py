@@ -1,0 +1,96 @@
+"""End-to-end parity of the CUDA hourglass (tcgen05 convs + fused epilogues + arg-max) against the
+bf16-emulating CPU oracle on seeded weights and inputs.
+
+Parity for this half is UNPINNED w.r.t. the reference (no pretrained weights, see
+oracle/hourglass.py); what is pinned here is kernel == oracle arithmetic.  Both sides round at the
+same points, so the only difference is the fp32 summation order inside a convolution, which can
+flip a bf16 rounding now and then.  Tolerances: heat-map within 2% of its dynamic range, arg-max
+index identical wherever the oracle's peak is separated from the runner-up by more than that
+noise (reported: overall agreement), confidence within the same bound.  The reference's own test
+demands +-1 heat-map row (tests/test_df3d.py:171: atol=0.02).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import argmax as oargmax
+from oracle import hourglass as ohg
+
+
+@pytest.fixture(scope="module")
+def hgmod(lib_built):
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test needs a CUDA device")
+    from deepfly3d_b200 import hourglass
+
+    return hourglass
+
+
+def _compare(hgmod, stacks, H, W, B, seed, flip=None, float_input=False):
+    model = ohg.make_model(stacks, seed=seed)
+    img = ohg.to_uint8(ohg.synthetic_images(B, H, W, seed=seed + 1))
+    eng = hgmod.HourglassEngine(model.state_dict(), H, W, max_batch=max(B, 1))
+    fl = None if flip is None else torch.tensor(flip, dtype=torch.uint8)
+    x = ohg.preprocess_u8(img, flip=flip)
+    if float_input:
+        idx, conf, heat = eng.forward(ohg.preprocess_u8(img).cuda(), flip=None if fl is None else fl.cuda(), return_heatmap=True)
+    else:
+        idx, conf, heat = eng.forward(img.cuda(), flip=None if fl is None else fl.cuda(), return_heatmap=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = model(x, emulate_bf16=True)[-1]                       # (B,K,Hh,Wh) fp32
+    got = heat[..., :19].permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all()
+    rng_ = (ref.max() - ref.min()).item()
+    err = (got - ref).abs().max().item() / rng_
+    ref_idx, ref_conf = oargmax.heatmap_argmax(ref.numpy())
+    # decode of the kernel's own heat-map must be bit-exact (integer index, fp32 peak)
+    own_idx, own_conf = oargmax.heatmap_argmax(got.numpy())
+    assert np.array_equal(idx.cpu().numpy(), own_idx)
+    assert np.array_equal(conf.cpu().numpy(), own_conf)
+    agree = float((idx.cpu().numpy() == ref_idx).mean())
+    # where they disagree the two candidates must be a near tie in the oracle's map
+    flat = ref.flatten(2).numpy()
+    gi = idx.cpu().numpy()
+    gap = np.take_along_axis(flat, ref_idx[..., None].astype(np.int64), -1)[..., 0] - \
+        np.take_along_axis(flat, gi[..., None].astype(np.int64), -1)[..., 0]
+    eng.close()
+    return err, agree, float(gap.max() / rng_), float(np.abs(conf.cpu().numpy() - ref_conf).max() / rng_)
+
+
+def test_two_stack_reference_shape(hgmod):
+    """config 1 shape: 2 stacks, 256 x 512 input -> 64 x 128 heat-map, mirrored cameras included."""
+    err, agree, gap, cerr = _compare(hgmod, 2, 256, 512, 3, seed=0, flip=[False, True, True])
+    print(f"2-stack 256x512: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
+    assert err < 0.02 and gap < 0.02 and cerr < 0.02
+    assert agree > 0.9
+
+
+def test_eight_stack_benchmark_shape(hgmod):
+    """config 2 shape: 8 stacks, 256 x 256 input -> 64 x 64 heat-map."""
+    err, agree, gap, cerr = _compare(hgmod, 8, 256, 256, 2, seed=1)
+    print(f"8-stack 256x256: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
+    assert err < 0.03 and gap < 0.03 and cerr < 0.03
+    assert agree > 0.85
+
+
+def test_float_input_and_small_image(hgmod):
+    """(B,3,H,W) float32 input path, smallest supported map sizes (64 x 64 input -> 1 x 1 at the bottom)."""
+    err, agree, gap, cerr = _compare(hgmod, 2, 64, 64, 5, seed=2, float_input=True)
+    assert err < 0.02 and gap < 0.02
+
+
+def test_batch_larger_than_chunk_is_consistent(hgmod):
+    """Images are independent: results do not depend on the chunking of the batch."""
+    model = ohg.make_model(2, seed=3)
+    img = ohg.to_uint8(ohg.synthetic_images(9, 128, 128, seed=4)).cuda()
+    eng_a = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=9)
+    eng_b = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=8)   # chunk 8 -> 8 + 1
+    ia, ca = eng_a.forward(img)
+    ib0, cb0 = eng_b.forward(img[:8])
+    ib1, cb1 = eng_b.forward(img[8:])
+    torch.cuda.synchronize()
+    assert torch.equal(ia, torch.cat([ib0, ib1])) and torch.equal(ca, torch.cat([cb0, cb1]))
+    assert eng_a.launches(9) > 0
