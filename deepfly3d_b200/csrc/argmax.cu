@@ -127,8 +127,9 @@ argmax_nhwc_kernel(const float* __restrict__ hm, int npix, int Cpad, int K,
 extern "C" int df3d_heatmap_argmax(const void* hm_dev, int dtype, int B, int K, int H, int W,
                                    int32_t* idx_dev, float* conf_dev, void* stream) {
   using namespace df3d;
-  DF3D_REQUIRE(hm_dev && idx_dev && conf_dev, DF3D_EINVAL, "df3d_heatmap_argmax: null pointer");
   DF3D_REQUIRE(B >= 0 && K > 0 && H > 0 && W > 0, DF3D_EINVAL, "df3d_heatmap_argmax: bad shape");
+  if (B == 0) return DF3D_OK;  // empty batch: nothing to decode (pointers may be null)
+  DF3D_REQUIRE(hm_dev && idx_dev && conf_dev, DF3D_EINVAL, "df3d_heatmap_argmax: null pointer");
   DF3D_REQUIRE(dtype == 0 || dtype == 1, DF3D_EINVAL, "df3d_heatmap_argmax: dtype must be 0 (f32) or 1 (bf16)");
   DF3D_REQUIRE((long long)H * W < (1ll << 30), DF3D_EINVAL, "df3d_heatmap_argmax: plane too large");
   if (B == 0) return DF3D_OK;
@@ -144,8 +145,9 @@ extern "C" int df3d_heatmap_argmax(const void* hm_dev, int dtype, int B, int K, 
 extern "C" int df3d_heatmap_argmax_nhwc(const float* hm_dev, int B, int H, int W, int Cpad, int K,
                                         int32_t* idx_dev, float* conf_dev, void* stream) {
   using namespace df3d;
-  DF3D_REQUIRE(hm_dev && idx_dev && conf_dev, DF3D_EINVAL, "df3d_heatmap_argmax_nhwc: null pointer");
   DF3D_REQUIRE(B >= 0 && H > 0 && W > 0, DF3D_EINVAL, "df3d_heatmap_argmax_nhwc: bad shape");
+  if (B == 0) return DF3D_OK;
+  DF3D_REQUIRE(hm_dev && idx_dev && conf_dev, DF3D_EINVAL, "df3d_heatmap_argmax_nhwc: null pointer");
   DF3D_REQUIRE(Cpad % 4 == 0 && Cpad >= 4 && Cpad <= 32 && K >= 1 && K <= Cpad, DF3D_EINVAL,
                "df3d_heatmap_argmax_nhwc: need Cpad%%4==0, Cpad<=32, K<=Cpad");
   DF3D_REQUIRE(kArgmaxThreads % (Cpad / 4) == 0, DF3D_EINVAL, "df3d_heatmap_argmax_nhwc: Cpad/4 must divide 256");

@@ -11,6 +11,8 @@
 // GEMM launches and no elementwise pass.  All activations live in the caller's workspace; a
 // small free-list arena reuses buffers so the working set stays small.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -172,6 +174,7 @@ struct Op {
   char *in0 = nullptr, *in1 = nullptr, *out0 = nullptr, *out1 = nullptr;
   const float *scale = nullptr, *shift = nullptr;
   int H = 0, W = 0, C = 0;
+  double flops_per_image = 0.0;  // algorithmic 2*MAC of a conv op (real Cin/Cout, no padding)
 };
 
 struct Affine {  // index into the float blob
@@ -201,6 +204,10 @@ struct df3d_hg {
   std::vector<Op> ops;
   char* heat_ptr = nullptr;  // fp32 score tensor of the last stack inside the workspace
   int Hh = 0, Wh = 0;
+  // optional per-launch timing (bench / profiling only): events[chunk][op][2]
+  bool timing = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<int> timed_bc;  // images of each timed chunk of the last forward
 };
 
 namespace df3d {
@@ -313,13 +320,14 @@ struct Emitter {
   // K = taps*CinPad.  Outputs may be invalid tensors (skipped).
   void conv(const Tensor& in, size_t w_off, int taps, int CinPad, int CoutPad, int BN, Affine a1, bool relu1,
             const Tensor* residual, const Tensor* out_raw, const Affine* a2, const Tensor* out_act,
-            const Tensor* out_f32) {
+            const Tensor* out_f32, double flop_per_px) {
     ++n_ops;
     if (err) return;
     if (dry) return;
     Op op;
     op.kind = OP_CONV;
     op.BN = BN;
+    op.flops_per_image = flop_per_px * in.H * in.W;
     ConvParams& p = op.conv;
     memset(&p, 0, sizeof(p));
     int tw, th, nb;
@@ -364,6 +372,7 @@ struct Emitter {
   }
 
   static int bn_for(int cout_pad) { return cout_pad >= 256 ? 256 : cout_pad; }
+  static double fpp(const Convp& c) { return 2.0 * c.cin * c.cout * c.k * c.k; }
 
   // pre-activation bottleneck: x (raw) / xa = relu(bn1(x)) -> y (raw) [+ ya = relu(next_bn(y))]
   void bottleneck(const Bott& b, const Tensor& x, const Tensor& xa, const BNp* next_bn, Tensor* y, Tensor* ya) {
@@ -372,12 +381,12 @@ struct Emitter {
     size_t w1 = pack_weights(b.c1, P, b.inpl);
     Affine a1 = conv_affine(b.c1, &b.bn2, P);
     Tensor t1 = talloc(H, W, P);
-    conv(xa, w1, 1, b.inpl, P, bn_for(P), a1, true, nullptr, &t1, nullptr, nullptr, nullptr);
+    conv(xa, w1, 1, b.inpl, P, bn_for(P), a1, true, nullptr, &t1, nullptr, nullptr, nullptr, fpp(b.c1));
     // conv2 (3x3) with bn3+relu folded
     size_t w2 = pack_weights(b.c2, P, P);
     Affine a2 = conv_affine(b.c2, &b.bn3, P);
     Tensor t2 = talloc(H, W, P);
-    conv(t1, w2, 9, P, P, bn_for(P), a2, true, nullptr, &t2, nullptr, nullptr, nullptr);
+    conv(t1, w2, 9, P, P, bn_for(P), a2, true, nullptr, &t2, nullptr, nullptr, nullptr, fpp(b.c2));
     tfree(t1);
     // projection shortcut on the raw input
     Tensor d;
@@ -386,7 +395,7 @@ struct Emitter {
       size_t wd = pack_weights(b.ds, O, b.inpl);
       Affine ad = conv_affine(b.ds, nullptr, O);
       d = talloc(H, W, O);
-      conv(x, wd, 1, b.inpl, O, bn_for(O), ad, false, nullptr, &d, nullptr, nullptr, nullptr);
+      conv(x, wd, 1, b.inpl, O, bn_for(O), ad, false, nullptr, &d, nullptr, nullptr, nullptr, fpp(b.ds));
       res = &d;
     }
     // conv3 (1x1) + residual, optionally emitting the next block's activated input
@@ -400,7 +409,7 @@ struct Emitter {
     } else {
       *ya = Tensor();
     }
-    conv(t2, w3, 1, P, O, bn_for(O), a3, false, res, y, next_bn ? &an : nullptr, ya, nullptr);
+    conv(t2, w3, 1, P, O, bn_for(O), a3, false, res, y, next_bn ? &an : nullptr, ya, nullptr, fpp(b.c3));
     tfree(t2);
     tfree(d);
   }
@@ -492,7 +501,7 @@ struct Emitter {
     Affine a0 = conv_affine(net.conv1, &net.bn1, kInplanes);
     Affine a0n = bn_affine(net.layer1.bn1, kInplanes);
     Tensor x = talloc(H2, W2, kInplanes), xa = talloc(H2, W2, kInplanes);
-    conv(col, w0, 1, kStemKPadCols, kInplanes, 64, a0, true, nullptr, &x, &a0n, &xa, nullptr);
+    conv(col, w0, 1, kStemKPadCols, kInplanes, 64, a0, true, nullptr, &x, &a0n, &xa, nullptr, fpp(net.conv1));
     tfree(col);
 
     Tensor y1, none;
@@ -524,13 +533,13 @@ struct Emitter {
       size_t wf = pack_weights(s.fc, kCh, kCh);
       Affine af = conv_affine(s.fc, &s.fc_bn, kCh);
       Tensor f = talloc(H4, W4, kCh);
-      conv(r, wf, 1, kCh, kCh, 256, af, true, nullptr, &f, nullptr, nullptr, nullptr);
+      conv(r, wf, 1, kCh, kCh, 256, af, true, nullptr, &f, nullptr, nullptr, nullptr, fpp(s.fc));
       tfree(r);
       if (i == S - 1) {
         size_t wsc = pack_weights(s.score, kHeatPad, kCh);
         Affine as = conv_affine(s.score, nullptr, kHeatPad);
         Tensor heat = talloc(H4, W4, kHeatPad, 4);
-        conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat);
+        conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat, fpp(s.score));
         tfree(f);
         if (!dry && !err) {
           Op op;
@@ -550,12 +559,12 @@ struct Emitter {
         size_t wsc = pack_weights(s.score, 64, kCh);
         Affine as = conv_affine(s.score, nullptr, 64);
         Tensor sc = talloc(H4, W4, 64);
-        conv(f, wsc, 1, kCh, 64, 64, as, false, nullptr, &sc, nullptr, nullptr, nullptr);
+        conv(f, wsc, 1, kCh, 64, 64, as, false, nullptr, &sc, nullptr, nullptr, nullptr, fpp(s.score));
         // u = fc_(f) + x
         size_t wf_ = pack_weights(s.fc_, kCh, kCh);
         Affine af_ = conv_affine(s.fc_, nullptr, kCh);
         Tensor u = talloc(H4, W4, kCh);
-        conv(f, wf_, 1, kCh, kCh, 256, af_, false, &x0, &u, nullptr, nullptr, nullptr);
+        conv(f, wf_, 1, kCh, kCh, 256, af_, false, &x0, &u, nullptr, nullptr, nullptr, fpp(s.fc_));
         tfree(f);
         tfree(x0);
         tfree(x0a);
@@ -565,7 +574,7 @@ struct Emitter {
         Affine an = bn_affine(net.stacks[i + 1].hg[kDepth - 1][0].bn1, kCh);
         x0 = talloc(H4, W4, kCh);
         x0a = talloc(H4, W4, kCh);
-        conv(sc, ws_, 1, 64, kCh, 256, as_, false, &u, &x0, &an, &x0a, nullptr);
+        conv(sc, ws_, 1, 64, kCh, 256, as_, false, &u, &x0, &an, &x0a, nullptr, fpp(s.score_));
         tfree(u);
         tfree(sc);
       }
@@ -605,6 +614,10 @@ static int chunk_for(const df3d_hg_desc& d) {
   long long px = (long long)d.in_h * d.in_w;
   int c = (int)((128ll * 256 * 256) / px);
   if (c < 8) c = 8;
+  if (const char* env = getenv("DF3D_HG_CHUNK")) {  // tuning / test knob: images per launch sequence
+    const int v = atoi(env);
+    if (v >= 1) c = v;
+  }
   if (c > d.max_batch) c = d.max_batch;
   return c;
 }
@@ -674,6 +687,7 @@ extern "C" void df3d_hg_destroy(df3d_hg* hg) {
   if (!hg) return;
   if (hg->d_w) cudaFree(hg->d_w);
   if (hg->d_a) cudaFree(hg->d_a);
+  for (cudaEvent_t ev : hg->events) cudaEventDestroy(ev);
   delete hg;
 }
 
@@ -712,9 +726,23 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
   const size_t img_stride = dtype == 0 ? (size_t)d.in_h * d.in_w : (size_t)3 * d.in_h * d.in_w * sizeof(float);
   const size_t heat_elems = (size_t)hg->Hh * hg->Wh * kHeatPad;
 
+  const size_t n_ops = hg->ops.size();
+  if (hg->timing) {
+    const size_t chunks = (size_t)(B + hg->chunk - 1) / hg->chunk;
+    while (hg->events.size() < chunks * n_ops * 2) {
+      cudaEvent_t ev;
+      DF3D_CUDA(cudaEventCreate(&ev));
+      hg->events.push_back(ev);
+    }
+    hg->timed_bc.clear();
+  }
   for (int c0 = 0; c0 < B; c0 += hg->chunk) {
     const int bc = (B - c0) < hg->chunk ? (B - c0) : hg->chunk;
-    for (const Op& op : hg->ops) {
+    const size_t ev_base = hg->timing ? hg->timed_bc.size() * n_ops * 2 : 0;
+    if (hg->timing) hg->timed_bc.push_back(bc);
+    for (size_t oi = 0; oi < n_ops; ++oi) {
+      const Op& op = hg->ops[oi];
+      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi], s));
       switch (op.kind) {
         case OP_IM2COL: {
           const char* img = static_cast<const char*>(images_dev) + (size_t)c0 * img_stride;
@@ -752,8 +780,58 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
                                       cudaMemcpyDeviceToDevice, s));
           break;
       }
+      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi + 1], s));
     }
   }
+  return DF3D_OK;
+}
+
+extern "C" int df3d_hg_set_timing(df3d_hg* hg, int enable) {
+  DF3D_REQUIRE(hg, DF3D_EINVAL, "df3d_hg_set_timing: null handle");
+  hg->timing = enable != 0;
+  if (!hg->timing) {
+    for (cudaEvent_t ev : hg->events) cudaEventDestroy(ev);
+    hg->events.clear();
+    hg->timed_bc.clear();
+  }
+  return DF3D_OK;
+}
+
+extern "C" int df3d_hg_read_timing(df3d_hg* hg, double* out8) {
+  DF3D_REQUIRE(hg && out8, DF3D_EINVAL, "df3d_hg_read_timing: null pointer");
+  DF3D_REQUIRE(hg->timing && !hg->timed_bc.empty(), DF3D_EINVAL, "df3d_hg_read_timing: no timed forward recorded");
+  const size_t n_ops = hg->ops.size();
+  double conv_ms = 0, conv_flops = 0, other_ms = 0, conv3_ms = 0, conv3_flops = 0;
+  int conv_n = 0, other_n = 0, conv3_n = 0;
+  for (size_t ci = 0; ci < hg->timed_bc.size(); ++ci) {
+    for (size_t oi = 0; oi < n_ops; ++oi) {
+      float ms = 0.f;
+      DF3D_CUDA(cudaEventSynchronize(hg->events[(ci * n_ops + oi) * 2 + 1]));
+      DF3D_CUDA(cudaEventElapsedTime(&ms, hg->events[(ci * n_ops + oi) * 2], hg->events[(ci * n_ops + oi) * 2 + 1]));
+      const Op& op = hg->ops[oi];
+      if (op.kind == OP_CONV) {
+        conv_ms += ms;
+        conv_flops += op.flops_per_image * hg->timed_bc[ci];
+        ++conv_n;
+        if (op.conv.taps == 9) {
+          conv3_ms += ms;
+          conv3_flops += op.flops_per_image * hg->timed_bc[ci];
+          ++conv3_n;
+        }
+      } else {
+        other_ms += ms;
+        ++other_n;
+      }
+    }
+  }
+  out8[0] = conv_ms;
+  out8[1] = conv_flops;
+  out8[2] = conv_n;
+  out8[3] = other_ms;
+  out8[4] = other_n;
+  out8[5] = conv3_ms;
+  out8[6] = conv3_flops;
+  out8[7] = conv3_n;
   return DF3D_OK;
 }
 

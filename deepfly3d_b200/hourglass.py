@@ -134,6 +134,17 @@ class HourglassEngine:
             return idx, conf, heat
         return idx, conf
 
+    def set_timing(self, enable):
+        check(lib.df3d_hg_set_timing(self._h, int(bool(enable))))
+
+    def read_timing(self):
+        """Per-kernel-class device times of the last forward (see df3d_hg_read_timing)."""
+        out = (C.c_double * 8)()
+        check(lib.df3d_hg_read_timing(self._h, out))
+        keys = ("conv_ms", "conv_flop", "conv_launches", "other_ms", "other_launches", "conv3x3_ms", "conv3x3_flop",
+                "conv3x3_launches")
+        return dict(zip(keys, list(out)))
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             lib.df3d_hg_destroy(self._h)

@@ -1,0 +1,141 @@
+"""df2d-compatible 2-D inference entry point backed by the CUDA hourglass.
+
+``inference_folder`` keeps the signature and return convention of
+``df2d.inference.inference_folder`` as called at df3d/core.py:177-185:
+
+    points2d (7, T, 19, 2)  float64, (row / Hh, col / Wh) of the arg-max in the (possibly mirrored)
+                            network frame
+    conf     (7, T, 19, 1)  float32 peak value
+
+Image ingest (JPEG decode + resize on the host) is the reference's path too and is not part of
+the accelerated hot path.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .hourglass import HourglassEngine
+from .skeleton import HEATMAP_SHAPE, NUM_CAMERAS, NUM_PREDICT
+
+_ENGINES = {}
+
+
+def image_name(folder, cam_id, img_id):
+    plain = os.path.join(folder, f"camera_{cam_id}_img_{img_id}.jpg")
+    if os.path.isfile(plain):
+        return plain
+    return os.path.join(folder, f"camera_{cam_id}_img_{img_id:06d}.jpg")
+
+
+def load_images(folder, max_img_id, size_hw, pin_memory=True):
+    """-> uint8 tensor (7, T, H, W) gray, resized to the network input."""
+    import cv2
+
+    T = max_img_id + 1
+    H, W = size_hw
+    out = torch.empty((NUM_CAMERAS, T, H, W), dtype=torch.uint8)
+    if pin_memory and torch.cuda.is_available():
+        out = out.pin_memory()
+    arr = out.numpy()
+    for c in range(NUM_CAMERAS):
+        for t in range(T):
+            path = image_name(folder, c, t)
+            img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+            if img is None:
+                raise FileNotFoundError(f"cannot read {path}")
+            if img.shape != (H, W):
+                img = cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR)
+            arr[c, t] = img
+    return out
+
+
+def random_state_dict(num_stacks=2, num_classes=NUM_PREDICT, seed=0):
+    """Seeded stand-in weights with the checkpoint's key layout (no pretrained weights offline)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k, scale=1.0):
+        sd[f"{name}.weight"] = torch.randn((co, ci, k, k), generator=g) * (scale / (ci * k * k) ** 0.5)
+        sd[f"{name}.bias"] = torch.randn(co, generator=g) * 0.05
+
+    def bn(name, n):
+        sd[f"{name}.weight"] = 1.0 + 0.1 * torch.randn(n, generator=g)
+        sd[f"{name}.bias"] = 0.1 * torch.randn(n, generator=g)
+        sd[f"{name}.running_mean"] = 0.1 * torch.randn(n, generator=g)
+        sd[f"{name}.running_var"] = 1.0 + 0.1 * torch.rand(n, generator=g)
+
+    def bott(name, inpl, planes):
+        bn(f"{name}.bn1", inpl); conv(f"{name}.conv1", planes, inpl, 1)
+        bn(f"{name}.bn2", planes); conv(f"{name}.conv2", planes, planes, 3)
+        bn(f"{name}.bn3", planes); conv(f"{name}.conv3", 2 * planes, planes, 1, 0.3)
+        if inpl != 2 * planes:
+            conv(f"{name}.downsample.0", 2 * planes, inpl, 1)
+
+    conv("conv1", 64, 3, 7); bn("bn1", 64)
+    bott("layer1.0", 64, 64); bott("layer2.0", 128, 64); bott("layer3.0", 128, 128)
+    for i in range(num_stacks):
+        for d in range(4):
+            for k in range(4 if d == 0 else 3):
+                bott(f"hg.{i}.hg.{d}.{k}.0", 256, 128)
+        bott(f"res.{i}.0", 256, 128)
+        conv(f"fc.{i}.0", 256, 256, 1); bn(f"fc.{i}.1", 256)
+        conv(f"score.{i}", num_classes, 256, 1)
+        if i < num_stacks - 1:
+            conv(f"fc_.{i}", 256, 256, 1, 0.1); conv(f"score_.{i}", 256, num_classes, 1, 0.1)
+    return sd
+
+
+def load_state_dict(weights=None):
+    """Checkpoint path (torch file holding a state_dict, possibly under 'state_dict') or
+    $DF3D_B200_WEIGHTS; without either, seeded stand-in weights are used and a warning is logged."""
+    path = weights or os.environ.get("DF3D_B200_WEIGHTS")
+    if path:
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        return ck["state_dict"] if isinstance(ck, dict) and "state_dict" in ck else ck
+    import logging
+
+    logging.getLogger("df3d.logger").warning(
+        "no pretrained hourglass weights given (weights= / $DF3D_B200_WEIGHTS): using seeded random weights")
+    return random_state_dict()
+
+
+def get_engine(state_dict, in_h, in_w, max_batch, device="cuda"):
+    key = (id(state_dict), in_h, in_w, device)
+    eng = _ENGINES.get(key)
+    if eng is None or eng.max_batch < max_batch:
+        eng = HourglassEngine(state_dict, in_h, in_w, max_batch, device=device)
+        _ENGINES[key] = eng
+    return eng
+
+
+def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return_confidence=True, max_img_id=None,
+                     batch_size=8, disable_pin_memory=False, state_dict=None, weights=None, input_size=None,
+                     device="cuda"):
+    """Runs the hourglass on every camera_{0..6}_img_{0..max_img_id}.jpg of `folder`."""
+    if max_img_id is None:
+        raise ValueError("max_img_id is required")
+    Hh, Wh = HEATMAP_SHAPE
+    in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
+    T = max_img_id + 1
+    images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory)
+    sd = state_dict if state_dict is not None else load_state_dict(weights)
+    # batch_size is the reference's DataLoader batch; here the whole folder is one device batch and
+    # the engine chunks internally, so it only bounds the workspace for tiny folders
+    eng = get_engine(sd, in_h, in_w, max(NUM_CAMERAS * T, batch_size), device=device)
+    flip = torch.zeros((NUM_CAMERAS, T), dtype=torch.uint8)
+    for c in camera_ids_to_flip:
+        flip[int(c)] = 1
+    dev_images = images.reshape(NUM_CAMERAS * T, in_h, in_w).to(device, non_blocking=True)
+    res = eng.forward(dev_images, flip=flip.reshape(-1).to(device), return_heatmap=return_heatmap)
+    idx, conf = res[0], res[1]
+    idx_h = idx.cpu().numpy().astype(np.int64).reshape(NUM_CAMERAS, T, -1)
+    hh, hw = eng.heatmap_shape
+    points2d = np.stack([(idx_h // hw) / hh, (idx_h % hw) / hw], axis=-1).astype(np.float64)
+    out = [points2d]
+    if return_heatmap:
+        K = eng.num_classes
+        out.append(res[2][..., :K].permute(0, 3, 1, 2).reshape(NUM_CAMERAS, T, K, hh, hw).cpu().numpy())
+    if return_confidence:
+        out.append(conf.cpu().numpy().reshape(NUM_CAMERAS, T, -1, 1))
+    return tuple(out) if len(out) > 1 else out[0]

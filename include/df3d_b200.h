@@ -197,6 +197,14 @@ int df3d_conv2d_nhwc_bf16(const void* in_dev, int B, int H, int W, int Cin, cons
                           const void* residual_dev, void* out_dev, const float* scale2_host,
                           const float* shift2_host, void* out_act_dev, void* stream);
 
+/* Optional per-launch timing for bench.py / profiling (NOT for production runs: it creates CUDA
+ * events).  When enabled, every kernel of df3d_hg_forward_argmax is bracketed by events on the
+ * launching stream; df3d_hg_read_timing synchronises them and returns, for the last forward,
+ *   out8 = { conv_gemm ms, conv_gemm algorithmic FLOP, conv_gemm launches,
+ *            other kernels ms, other launches, 3x3-conv ms, 3x3-conv FLOP, 3x3-conv launches }. */
+int df3d_hg_set_timing(df3d_hg* hg, int enable);
+int df3d_hg_read_timing(df3d_hg* hg, double* out8);
+
 /* number of kernels one df3d_hg_forward_argmax call launches (for bench.py's gpu_launches) */
 int df3d_hg_launches_per_forward(const df3d_hg* hg, int B);
 

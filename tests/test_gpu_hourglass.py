@@ -6,8 +6,9 @@ oracle/hourglass.py); what is pinned here is kernel == oracle arithmetic.  Both 
 same points, so the only difference is the fp32 summation order inside a convolution, which can
 flip a bf16 rounding now and then.  Tolerances: heat-map within 2% of its dynamic range, arg-max
 index identical wherever the oracle's peak is separated from the runner-up by more than that
-noise (reported: overall agreement), confidence within the same bound.  The reference's own test
-demands +-1 heat-map row (tests/test_df3d.py:171: atol=0.02).
+noise, confidence within the same bound.  With seeded random weights the maps are noise-like, so
+many peaks are near ties (overall agreement is printed, not asserted tightly).  The reference's
+own test demands +-1 heat-map row (tests/test_df3d.py:171: atol=0.02).
 """
 import numpy as np
 import pytest
@@ -56,7 +57,14 @@ def _compare(hgmod, stacks, H, W, B, seed, flip=None, float_input=False):
     gi = idx.cpu().numpy()
     gap = np.take_along_axis(flat, ref_idx[..., None].astype(np.int64), -1)[..., 0] - \
         np.take_along_axis(flat, gi[..., None].astype(np.int64), -1)[..., 0]
+    # integer-exact wherever the oracle's peak beats its runner-up by more than twice the
+    # measured heat-map deviation (a flip would need both values to move against each other)
+    top2 = np.sort(flat, axis=-1)[..., -2]
+    margin = np.take_along_axis(flat, ref_idx[..., None].astype(np.int64), -1)[..., 0] - top2
+    clear = margin > 2.0 * err * rng_
+    assert np.array_equal(gi[clear], ref_idx[clear]), "arg-max differs on a well-separated peak"
     eng.close()
+    print(f"  well-separated peaks: {clear.mean():.3f} of joints, all identical")
     return err, agree, float(gap.max() / rng_), float(np.abs(conf.cpu().numpy() - ref_conf).max() / rng_)
 
 
@@ -65,7 +73,7 @@ def test_two_stack_reference_shape(hgmod):
     err, agree, gap, cerr = _compare(hgmod, 2, 256, 512, 3, seed=0, flip=[False, True, True])
     print(f"2-stack 256x512: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
     assert err < 0.02 and gap < 0.02 and cerr < 0.02
-    assert agree > 0.9
+    assert agree > 0.7
 
 
 def test_eight_stack_benchmark_shape(hgmod):
@@ -73,7 +81,7 @@ def test_eight_stack_benchmark_shape(hgmod):
     err, agree, gap, cerr = _compare(hgmod, 8, 256, 256, 2, seed=1)
     print(f"8-stack 256x256: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
     assert err < 0.03 and gap < 0.03 and cerr < 0.03
-    assert agree > 0.85
+    assert agree > 0.6
 
 
 def test_float_input_and_small_image(hgmod):
@@ -82,15 +90,16 @@ def test_float_input_and_small_image(hgmod):
     assert err < 0.02 and gap < 0.02
 
 
-def test_batch_larger_than_chunk_is_consistent(hgmod):
-    """Images are independent: results do not depend on the chunking of the batch."""
+def test_batch_larger_than_chunk_is_consistent(hgmod, monkeypatch):
+    """Images are independent: results do not depend on how the batch is cut into chunks
+    (ragged last chunk, partially filled multi-image M tiles on the 8x8 / 4x4 / 2x2 levels)."""
     model = ohg.make_model(2, seed=3)
-    img = ohg.to_uint8(ohg.synthetic_images(9, 128, 128, seed=4)).cuda()
-    eng_a = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=9)
-    eng_b = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=8)   # chunk 8 -> 8 + 1
+    img = ohg.to_uint8(ohg.synthetic_images(11, 128, 128, seed=4)).cuda()
+    eng_a = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=11)
     ia, ca = eng_a.forward(img)
-    ib0, cb0 = eng_b.forward(img[:8])
-    ib1, cb1 = eng_b.forward(img[8:])
+    monkeypatch.setenv("DF3D_HG_CHUNK", "4")                                   # 4 + 4 + 3
+    eng_b = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=11)
+    ib, cb = eng_b.forward(img)
     torch.cuda.synchronize()
-    assert torch.equal(ia, torch.cat([ib0, ib1])) and torch.equal(ca, torch.cat([cb0, cb1]))
-    assert eng_a.launches(9) > 0
+    assert torch.equal(ia, ib) and torch.equal(ca, cb)
+    assert eng_b.launches(11) == 3 * eng_a.launches(11)
