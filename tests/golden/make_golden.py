@@ -9,6 +9,9 @@ Sources (all under /root/reference):
   tests/data/reference_df3d/df3d_result_2d.pkl     -> result_2d.npz     (input of test_calibration, test_df3d.py:213-214)
   tests/data/reference_df3d/df3d_result_3d.pkl     -> result_3d.npz     (expected of test_calibration, test_df3d.py:221-243)
 
+  tests/data/reference/camera_{0..6}_img_{0..2}.jpg -> images/          (21 of the 105 sample JPEGs, plumbing input
+                                                                         of test_pose_estimation, test_df3d.py:150-160)
+
 The pickles are converted to plain ``.npz`` so that no reference class is needed
 to load them.  ``calib.npz`` and ``template.npz`` are also copied into
 ``deepfly3d_b200/data/`` because the product path needs them at run time exactly
@@ -61,6 +64,14 @@ def main():
         heatmap_confidence=r3["heatmap_confidence"],
         **cams_to_arrays(r3),
     )
+
+    img_dir = os.path.join(HERE, "images")
+    os.makedirs(img_dir, exist_ok=True)
+    for cam in range(7):
+        for img_id in range(3):
+            name = f"camera_{cam}_img_{img_id}.jpg"
+            shutil.copy(f"{REF}/tests/data/reference/{name}", os.path.join(img_dir, name))
+            os.chmod(os.path.join(img_dir, name), 0o644)
 
     os.makedirs(PKG_DATA, exist_ok=True)
     for name in ("calib.npz", "template.npz"):

@@ -1,0 +1,122 @@
+"""The df3d.core.Core surface end to end on the GPU (mirrors the reference's test_pose_estimation
+and test_calibration, tests/test_df3d.py:150-244, on the committed fixtures)."""
+import os
+import pickle
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import argmax as oargmax
+from oracle import hourglass as ohg
+from oracle import pack as opack
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+IMAGES = os.path.join(HERE, "golden", "images")
+
+
+@pytest.fixture()
+def working(tmp_path, lib_built):
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test needs a CUDA device")
+    d = tmp_path / "sample" / "test"          # 'sample/test' also exercises the default-ordering regex
+    d.mkdir(parents=True)
+    for f in os.listdir(IMAGES):
+        shutil.copy(os.path.join(IMAGES, f), d / f)
+    return str(d)
+
+
+def test_core_loads_folder(working):
+    from deepfly3d_b200.core import Core
+
+    core = Core(input_folder=working, output_folder=working + "_out", num_images_max=0, camera_ordering=None)
+    assert core.num_images == 3 and core.max_img_id == 2
+    assert core.image_shape == [960, 480]
+    assert np.all(core.camera_ordering == np.arange(7))
+    assert core.save_path.endswith("df3d_result_{}.pkl".format(working.replace("/", "_")))
+    with pytest.raises(FileNotFoundError):
+        os.makedirs(working + "_empty")
+        Core(input_folder=working + "_empty")
+
+
+def test_pose_estimation_matches_oracle(working):
+    """Images -> hourglass -> arg-max -> packing through Core, against the CPU oracle fed the same
+    JPEGs and the same (seeded) weights; tolerance of the reference test: atol 0.02 on points2d."""
+    import cv2
+
+    from deepfly3d_b200.core import Core
+
+    model = ohg.make_model(2, seed=0)
+    core = Core(input_folder=working, num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6], state_dict=model.state_dict())
+    core.pose2d_estimation()
+    assert core.points2d.shape == (7, 3, 38, 2) and core.conf.shape == (7, 3, 19, 1)
+
+    imgs = np.stack([[cv2.resize(cv2.imread(os.path.join(working, f"camera_{c}_img_{t}.jpg"), cv2.IMREAD_GRAYSCALE),
+                                 (512, 256), interpolation=cv2.INTER_LINEAR) for t in range(3)] for c in range(7)])
+    flip = np.zeros((7, 3), dtype=bool)
+    flip[4:] = True
+    with torch.no_grad():
+        x = ohg.preprocess_u8(torch.as_tensor(imgs.reshape(21, 256, 512)), flip=flip.reshape(-1))
+        heat = model(x, emulate_bf16=True)[-1]
+    idx, conf = oargmax.heatmap_argmax(heat.numpy())
+    ref = opack.pack_points2d(opack.indices_to_points2d(idx.reshape(7, 3, 19), (64, 128)), range(7))
+    # structure is exact (zeros, (0,1) quirk, camera 3 dropped); coordinates within one heat-map cell
+    assert np.array_equal(core.points2d == 0, ref == 0) or np.abs(core.points2d - ref).max() <= 0.02
+    close = np.abs(core.points2d - ref).max(axis=-1) <= 0.02
+    assert close.mean() > 0.8, f"only {close.mean():.3f} of the joints within atol 0.02 of the oracle"
+    rngv = float(heat.max() - heat.min())
+    assert np.abs(core.conf.reshape(21, 19) - conf).max() < 0.02 * rngv
+    core.save()
+    with open(core.save_path, "rb") as f:
+        saved = pickle.load(f)
+    assert set(saved) == {"points2d", "camera_ordering", "heatmap_confidence"}      # 2-D only: no calibration yet
+
+
+def test_calibration_matches_golden(working, golden):
+    """Reference test_calibration: golden 2-D in, BA + DLT + procrustes, compare with golden 3-D.
+    North-star tolerance 1e-3 mm on the joints (the reference's SciPy path gets 1e-5)."""
+    from deepfly3d_b200.core import Core
+
+    core = Core(input_folder=working, num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6])
+    core.points2d = golden["result_2d"]["points2d"]
+    core.conf = golden["result_2d"]["heatmap_confidence"]
+    core.calibrate_calc(0, 100)
+    core.save()
+    with open(core.save_path, "rb") as f:
+        saved = pickle.load(f)
+    r3 = golden["result_3d"]
+    assert set(saved) == {0, 1, 2, 3, 4, 5, 6, "points3d", "points2d", "points3d_wo_procrustes", "camera_ordering",
+                          "heatmap_confidence"}
+    np.testing.assert_allclose(saved["points3d_wo_procrustes"], r3["points3d_wo_procrustes"], atol=1e-3)
+    np.testing.assert_allclose(saved["points3d"], r3["points3d"], atol=1e-3)
+    for cam in range(7):
+        np.testing.assert_allclose(saved[cam]["R"], r3["R"][cam], atol=1e-3)
+        np.testing.assert_allclose(saved[cam]["tvec"], r3["tvec"][cam], atol=5e-3)
+        np.testing.assert_array_equal(saved[cam]["intr"], r3["intr"][cam])
+        np.testing.assert_array_equal(saved[cam]["distort"], r3["distort"][cam])
+    np.testing.assert_array_equal(saved[3]["R"], golden["calib"]["R"][3])              # untouched camera
+    # resume from the pickle (core.py:108-126)
+    again = Core(input_folder=working, num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6])
+    assert again.camNet is not None and again.has_calibration
+    np.testing.assert_allclose(again.camNet.points3d, saved["points3d_wo_procrustes"], atol=1e-9)
+
+
+def test_pipeline_matches_stagewise(golden):
+    """Pose3DPipeline (what bench.py times) == the stages called one by one."""
+    from deepfly3d_b200 import ops
+    from deepfly3d_b200.inference import random_state_dict
+    from deepfly3d_b200.pipeline import Pose3DPipeline
+
+    T = 4
+    pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * T, image_shape=[960, 480])
+    img = ohg.to_uint8(ohg.synthetic_images(7 * T, 128, 128, seed=5)).cuda()
+    out = pipe.run(img, T)
+    idx, conf = pipe.engine.forward(img, flip=pipe.flip_flags(T))
+    p2d, pxy = ops.pack_points2d(idx, 7, T, (32, 32), range(7), [960, 480])
+    torch.cuda.synchronize()
+    assert torch.equal(out["idx"], idx) and torch.equal(out["points2d"], p2d) and torch.equal(out["pts_xy"], pxy)
+    assert out["points3d_wo_procrustes"].shape == (T, 38, 3) and torch.isfinite(out["points3d_wo_procrustes"]).all()
+    assert pipe.launches(7 * T) > 100
