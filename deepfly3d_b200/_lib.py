@@ -56,6 +56,8 @@ SIGNATURES = {
     "df3d_hg_launches_per_forward": (_i, [_vp, _i]),
     "df3d_hg_set_timing": (_i, [_vp, _i]),
     "df3d_hg_read_timing": (_i, [_vp, _vp]),
+    "df3d_hg_num_ops": (_i, [_vp]),
+    "df3d_hg_op_timing": (_i, [_vp, _i, _vp, _vp, _vp, C.c_char_p, _i]),
     "df3d_hg_set_mean": (_i, [_vp, C.c_float, C.c_float, C.c_float]),
     "df3d_conv2d_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

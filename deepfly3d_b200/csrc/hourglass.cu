@@ -835,6 +835,51 @@ extern "C" int df3d_hg_read_timing(df3d_hg* hg, double* out8) {
   return DF3D_OK;
 }
 
+extern "C" int df3d_hg_num_ops(const df3d_hg* hg) { return hg ? (int)hg->ops.size() : 0; }
+
+// per-op device time (ms, summed over the chunks of the last timed forward) + a one-line description
+extern "C" int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, double* flops_out, double* bytes_out,
+                                 char* desc, int desc_len) {
+  DF3D_REQUIRE(hg && ms_out && flops_out && bytes_out && desc, DF3D_EINVAL, "df3d_hg_op_timing: null pointer");
+  DF3D_REQUIRE(hg->timing && !hg->timed_bc.empty(), DF3D_EINVAL, "df3d_hg_op_timing: no timed forward recorded");
+  const size_t n_ops = hg->ops.size();
+  DF3D_REQUIRE(op_index >= 0 && (size_t)op_index < n_ops, DF3D_EINVAL, "df3d_hg_op_timing: bad op index");
+  const Op& op = hg->ops[op_index];
+  double ms = 0, images = 0;
+  for (size_t ci = 0; ci < hg->timed_bc.size(); ++ci) {
+    float t = 0.f;
+    DF3D_CUDA(cudaEventSynchronize(hg->events[(ci * n_ops + op_index) * 2 + 1]));
+    DF3D_CUDA(cudaEventElapsedTime(&t, hg->events[(ci * n_ops + op_index) * 2], hg->events[(ci * n_ops + op_index) * 2 + 1]));
+    ms += t;
+    images += hg->timed_bc[ci];
+  }
+  *ms_out = ms;
+  *flops_out = op.flops_per_image * images;
+  double bpi = 0;  // algorithmic HBM bytes per image of this op (activations in + out)
+  if (op.kind == OP_CONV) {
+    const ConvParams& p = op.conv;
+    const double px = (double)p.H * p.W;
+    bpi = px * 2.0 * (p.kc_per_tap * 64 + (p.residual ? p.res_ld : 0) + (p.out_raw ? p.raw_ld : 0) + (p.out_act ? p.act_ld : 0)) +
+          px * 4.0 * (p.out_f32 ? p.f32_ld : 0);
+    snprintf(desc, desc_len, "conv%dx%d %4dx%-4d cin=%3d BN=%3d%s%s%s", p.taps == 9 ? 3 : 1, p.taps == 9 ? 3 : 1, p.H, p.W,
+             p.kc_per_tap * 64, op.BN, p.residual ? " +res" : "", p.out_act ? " +act" : "", p.out_f32 ? " f32" : "");
+  } else if (op.kind == OP_POOL) {
+    bpi = (double)op.H * op.W * op.C * 2.0 * 1.5;
+    snprintf(desc, desc_len, "maxpool+bn  %4dx%-4d c=%3d", op.H, op.W, op.C);
+  } else if (op.kind == OP_UPADD) {
+    bpi = (double)op.H * op.W * op.C * 2.0 * 3.25;
+    snprintf(desc, desc_len, "upadd+bn    %4dx%-4d c=%3d", op.H, op.W, op.C);
+  } else if (op.kind == OP_IM2COL) {
+    bpi = (double)hg->desc.in_h * hg->desc.in_w + (double)hg->desc.in_h * hg->desc.in_w / 4 * kStemKPadCols * 2.0;
+    snprintf(desc, desc_len, "stem im2col");
+  } else {
+    bpi = (double)op.H * op.W * op.C * 4.0;
+    snprintf(desc, desc_len, "argmax      %4dx%-4d", op.H, op.W);
+  }
+  *bytes_out = bpi * images;
+  return DF3D_OK;
+}
+
 extern "C" int df3d_hg_set_mean(df3d_hg* hg, float m0, float m1, float m2) {
   DF3D_REQUIRE(hg, DF3D_EINVAL, "df3d_hg_set_mean: null handle");
   hg->mean[0] = m0;

@@ -145,6 +145,16 @@ class HourglassEngine:
                 "conv3x3_launches")
         return dict(zip(keys, list(out)))
 
+    def op_table(self):
+        """[(label, ms, flop, bytes)] per plan entry for the last timed forward."""
+        rows = []
+        buf = C.create_string_buffer(128)
+        for i in range(lib.df3d_hg_num_ops(self._h)):
+            ms, fl, by = C.c_double(), C.c_double(), C.c_double()
+            check(lib.df3d_hg_op_timing(self._h, i, C.byref(ms), C.byref(fl), C.byref(by), buf, 128))
+            rows.append((buf.value.decode(), ms.value, fl.value, by.value))
+        return rows
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             lib.df3d_hg_destroy(self._h)

@@ -204,6 +204,11 @@ int df3d_conv2d_nhwc_bf16(const void* in_dev, int B, int H, int W, int Cin, cons
  *            other kernels ms, other launches, 3x3-conv ms, 3x3-conv FLOP, 3x3-conv launches }. */
 int df3d_hg_set_timing(df3d_hg* hg, int enable);
 int df3d_hg_read_timing(df3d_hg* hg, double* out8);
+/* per-op view of the same timing: device ms, algorithmic FLOP and activation bytes of plan entry
+ * `op_index` (0 <= op_index < df3d_hg_num_ops) summed over the last timed forward, plus a label */
+int df3d_hg_num_ops(const df3d_hg* hg);
+int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, double* flops_out, double* bytes_out,
+                      char* desc, int desc_len);
 
 /* number of kernels one df3d_hg_forward_argmax call launches (for bench.py's gpu_launches) */
 int df3d_hg_launches_per_forward(const df3d_hg* hg, int B);
