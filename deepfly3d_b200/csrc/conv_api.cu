@@ -24,8 +24,8 @@ extern "C" int df3d_conv2d_nhwc_bf16(const void* in_dev, int B, int H, int W, in
   DF3D_REQUIRE(in_dev && w_host && scale1_host && shift1_host && out_dev, DF3D_EINVAL, "df3d_conv2d_nhwc_bf16: null pointer");
   DF3D_REQUIRE(ksize == 1 || ksize == 3, DF3D_EUNSUPPORTED, "df3d_conv2d_nhwc_bf16: ksize must be 1 or 3");
   DF3D_REQUIRE(Cin % 64 == 0 && Cin >= 64, DF3D_EUNSUPPORTED, "df3d_conv2d_nhwc_bf16: Cin must be a multiple of 64");
-  DF3D_REQUIRE(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256, DF3D_EUNSUPPORTED,
-               "df3d_conv2d_nhwc_bf16: Cout must be 32, 64, 128 or 256");
+  DF3D_REQUIRE(Cout == 64 || Cout == 128 || Cout == 256, DF3D_EUNSUPPORTED,
+               "df3d_conv2d_nhwc_bf16: Cout must be 64, 128 or 256");
   DF3D_REQUIRE(B >= 1 && H >= 1 && W >= 1, DF3D_EINVAL, "df3d_conv2d_nhwc_bf16: bad shape");
   DF3D_REQUIRE(!out_act_dev || (scale2_host && shift2_host), DF3D_EINVAL, "df3d_conv2d_nhwc_bf16: out_act needs scale2/shift2");
   int tw = W < 16 ? W : 16;
@@ -68,6 +68,9 @@ extern "C" int df3d_conv2d_nhwc_bf16(const void* in_dev, int B, int H, int W, in
   memset(&p, 0, sizeof(p));
   if (!rc) rc = make_tmap_act(&p.tmA, in_dev, Cin, W, H, B, tw, th, nb);
   if (!rc) rc = make_tmap_wgt(&p.tmB, d_w, (int)K, Cout, Cout);
+  if (!rc && residual_dev) rc = make_tmap_act(&p.tmRes, residual_dev, Cout, W, H, B, tw, th, nb);
+  if (!rc) rc = make_tmap_act(&p.tmRaw, out_dev, Cout, W, H, B, tw, th, nb);
+  if (!rc && out_act_dev) rc = make_tmap_act(&p.tmAct, out_act_dev, Cout, W, H, B, tw, th, nb);
   if (!rc) {
     p.taps = taps;
     p.kc_per_tap = Cin / 64;

@@ -5,10 +5,15 @@
 //     per (tap, channel block); the 3x3 halo / zero padding is the TMA's out-of-bounds zero fill
 //     (coordinates x0+dx-1, y0+dy-1 may be -1 or W/H).
 //   * B tile: BN output channels x 64 K, 2-D TMA from the packed [CoutPad][taps*CinPad] weights.
-//   * one CTA per SM, persistent over tiles; warp 0 = TMA producer, warp 1 = MMA issuer (one
-//     elected thread) + TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each).
-//   * TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps
-//     the MMAs of tile i+1.
+//   * one CTA per SM, persistent over tiles, 7 warps:
+//       warp 0  TMA producer of the A/B ring          warp 1  MMA issuer (one thread) + TMEM owner
+//       warp 2  TMA producer of the residual ring     warps 3..6  epilogue (one TMEM lane quarter each)
+//   * TMEM holds two accumulator stages (2 x BN fp32 columns): the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+//   * epilogue, per 64-channel slab: tcgen05.ld -> scale/shift (+ residual slab from shared memory,
+//     prefetched by TMA) -> ReLU / bf16 rounding -> 128B-swizzled shared-memory slab -> TMA store.
+//     Every global access of the kernel is a TMA bulk transfer (fully coalesced, asynchronous); the
+//     only direct stores left are the fp32 score maps of the last stack.
 #include "conv_gemm.cuh"
 #include "sm100.cuh"
 
@@ -16,18 +21,17 @@ namespace df3d {
 
 using namespace sm100;
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 224;
+constexpr int kEpiWarp0 = 3;            // first epilogue warp
+constexpr int kEpiThreads = 128;
 constexpr int kTileM = 128;
-constexpr int kABytes = kTileM * 128;  // 128 rows x 64 bf16
-
-template <int BN>
-struct ConvCfg {
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+constexpr int kABytes = kTileM * 128;   // 128 rows x 64 bf16
+constexpr int kSlabBytes = kTileM * 128;  // one 64-channel bf16 slab of an output / residual tile
+constexpr int kMaxStages = 8;
+constexpr int kMaxResSlots = 4;
+constexpr int kAffBytes = 4 * 256 * 4;  // scale1, shift1, scale2, shift2 for up to 256 channels
+constexpr int kBarBytes = 512;
+constexpr int kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -37,18 +41,30 @@ __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(_
 
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  constexpr int kBBytes = BN * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int kSlabs = BN >= 64 ? BN / 64 : 1;   // 64-channel slabs per tile (bf16 outputs)
+
   extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle needs 1024-byte aligned tiles
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  auto a_addr = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto b_addr = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle: 1024-byte aligned tiles
+  const int n_stages = p.n_stages, n_res = p.n_res_slots;
+  const bool has_res = n_res > 0, has_raw = p.out_raw != nullptr, has_act = p.out_act != nullptr;
+  // carve-up: [A/B ring][residual ring][raw out x2][act out x2][affine][barriers]
+  const uint32_t res_base = smem_base + n_stages * kStageBytes;
+  const uint32_t raw_base = res_base + n_res * kSlabBytes;
+  const uint32_t act_base = raw_base + (has_raw ? 2 * kSlabBytes : 0);
+  const uint32_t aff_base = act_base + (has_act ? 2 * kSlabBytes : 0);
+  const uint32_t bar_base = aff_base + kAffBytes;
+  auto a_addr = [&](int s) { return smem_base + s * kStageBytes; };
+  auto b_addr = [&](int s) { return smem_base + s * kStageBytes + kABytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + kMaxResSlots + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kMaxResSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -58,7 +74,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA);
     prefetch_tensormap(&p.tmB);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    if (has_res) prefetch_tensormap(&p.tmRes);
+    if (has_raw) prefetch_tensormap(&p.tmRaw);
+    if (has_act) prefetch_tensormap(&p.tmAct);
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -66,27 +85,53 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < n_res; ++s) {
+      mbar_init(rfull_bar(s), 1);
+      mbar_init(rempty_bar(s), 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  // per-channel epilogue constants -> shared memory (CoutPad <= 256)
+  {
+    const int ncol = p.n_tiles_n * BN;
+    for (int i = threadIdx.x; i < ncol; i += kConvThreads) {
+      float s1 = p.scale1[i], h1 = p.shift1[i], s2 = 0.f, h2 = 0.f;
+      if (has_act) {
+        s2 = p.scale2[i];
+        h2 = p.shift2[i];
+      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aff_base + 4u * i), "f"(s1));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aff_base + 1024u + 4u * i), "f"(h1));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aff_base + 2048u + 4u * i), "f"(s2));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aff_base + 3072u + 4u * i), "f"(h2));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  auto decode_tile = [&](int tile, int& nt, int& x0, int& y0, int& n0) {
+    nt = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    const int tx = mt % p.tiles_x;
+    mt /= p.tiles_x;
+    const int ty = mt % p.tiles_y;
+    const int tb = mt / p.tiles_y;
+    x0 = tx * p.tw;
+    y0 = ty * p.th;
+    n0 = tb * p.nb;
+  };
+
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ A/B producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tb = mt / p.tiles_y;
-        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.nb;
+        int nt, x0, y0, n0;
+        decode_tile(tile, nt, x0, y0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
           int dx = 0, dy = 0;
@@ -95,10 +140,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             dx = tap % 3 - 1;
           }
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           tma_load_4d(a_addr(stage), &p.tmA, full_bar(stage), kc * 64, x0 + dx, y0 + dy, n0);
           tma_load_2d(b_addr(stage), &p.tmB, full_bar(stage), kb * 64, nt * BN);
-          if (++stage == Cfg::kStages) {
+          if (++stage == (uint32_t)n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -124,7 +169,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
             umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
-          if (++stage == Cfg::kStages) {
+          if (++stage == (uint32_t)n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -132,103 +177,147 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
       }
     }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual producer
+    if (lane == 0 && has_res) {
+      uint32_t slot = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int nt, x0, y0, n0;
+        decode_tile(tile, nt, x0, y0, n0);
+        for (int sl = 0; sl < kSlabs; ++sl) {
+          mbar_wait(rempty_bar(slot), phase ^ 1u);
+          mbar_arrive_expect_tx(rfull_bar(slot), kSlabBytes);
+          tma_load_4d(res_base + slot * kSlabBytes, &p.tmRes, rfull_bar(slot), nt * BN + sl * 64, x0, y0, n0);
+          if (++slot == (uint32_t)n_res) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;
-    uint32_t it = 0;
+    // ------------------------------------------------------------------ epilogue (warps 3..6)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;       // row of the tile = pixel
+    const bool leader = (warp == kEpiWarp0) && (lane == 0);
+    const uint32_t row_off = (uint32_t)m * 128u;
+    const uint32_t sw = (uint32_t)(m & 7);
+    uint32_t it = 0, rslot = 0, rphase = 0, obuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tb = mt / p.tiles_y;
-      const int x = tx * p.tw + m % p.tw;
-      const int y = ty * p.th + (m / p.tw) % p.th;
-      const int n = tb * p.nb + m / (p.tw * p.th);
-      const bool valid = n < p.B;
-      const size_t pix = ((size_t)n * p.H + y) * p.W + x;
-
+      int nt, x0, y0, n0;
+      decode_tile(tile, nt, x0, y0, n0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+
+      if (p.out_f32) {
+        // fp32 score maps of the last stack (BN = 32): direct, predicated stores
+        const int x = x0 + m % p.tw, y = y0 + (m / p.tw) % p.th, n = n0 + m / (p.tw * p.th);
         uint32_t r[32];
-        tmem_ld_32x32(t_row + c0, r);
+        tmem_ld_32x32(t_row, r);
         tmem_ld_wait();
-        if (valid) {
-          const int cbase = nt * BN + c0;
+        if (n < p.B) {
+          float* o = p.out_f32 + (((size_t)n * p.H + y) * p.W + x) * p.f32_ld + nt * BN;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 8 channels at a time
-            const int c = cbase + j * 8;
-            float v[8];
-            const float4 s1a = __ldg(reinterpret_cast<const float4*>(p.scale1 + c));
-            const float4 s1b = __ldg(reinterpret_cast<const float4*>(p.scale1 + c + 4));
-            const float4 h1a = __ldg(reinterpret_cast<const float4*>(p.shift1 + c));
-            const float4 h1b = __ldg(reinterpret_cast<const float4*>(p.shift1 + c + 4));
-            const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
-            const float h1[8] = {h1a.x, h1a.y, h1a.z, h1a.w, h1b.x, h1b.y, h1b.z, h1b.w};
+          for (int j = 0; j < 8; ++j) {
+            float v[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[j * 8 + e]), s1[e], h1[e]);
-            if (p.residual) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + c));
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+            for (int e = 0; e < 4; ++e) {
+              const int c = nt * BN + j * 4 + e;
+              v[e] = fmaf(__uint_as_float(r[j * 4 + e]), lds_f32(aff_base + 4u * c), lds_f32(aff_base + 1024u + 4u * c));
+              if (p.relu1) v[e] = fmaxf(v[e], 0.0f);
+            }
+            reinterpret_cast<float4*>(o)[j] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int sl = 0; sl < kSlabs; ++sl) {
+          if (has_res) mbar_wait(rfull_bar(rslot), rphase);
+          const uint32_t rbuf = res_base + rslot * kSlabBytes + row_off;
+          const uint32_t raw_buf = raw_base + obuf * kSlabBytes + row_off;
+          const uint32_t act_buf = act_base + obuf * kSlabBytes + row_off;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(rh[e]);
-                v[2 * e] += f.x;
-                v[2 * e + 1] += f.y;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + sl * 64 + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // 8 channels = one 16-byte chunk of the swizzled row
+              const int c = nt * BN + sl * 64 + half * 32 + j * 8;
+              const uint32_t chunk = ((uint32_t)(half * 4 + j) ^ sw) << 4;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                v[e] = fmaf(__uint_as_float(r[j * 8 + e]), lds_f32(aff_base + 4u * (c + e)), lds_f32(aff_base + 1024u + 4u * (c + e)));
+              if (has_res) {
+                const uint4 rr = lds128(rbuf + chunk);
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(rh[e]);
+                  v[2 * e] += f.x;
+                  v[2 * e + 1] += f.y;
+                }
+              }
+              if (p.relu1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+              }
+              if (has_raw) {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                sts128(raw_buf + chunk, o);
+              }
+              if (has_act) {
+                float w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  w[e] = fmaxf(fmaf(bf16_round(v[e]), lds_f32(aff_base + 2048u + 4u * (c + e)), lds_f32(aff_base + 3072u + 4u * (c + e))), 0.0f);
+                uint4 o;
+                o.x = pack_bf16x2(w[0], w[1]);
+                o.y = pack_bf16x2(w[2], w[3]);
+                o.z = pack_bf16x2(w[4], w[5]);
+                o.w = pack_bf16x2(w[6], w[7]);
+                sts128(act_buf + chunk, o);
               }
             }
-            if (p.relu1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-            }
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.f32_ld + c);
-              o[0] = make_float4(v[0], v[1], v[2], v[3]);
-              o[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (p.out_raw) {
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.out_raw + pix * p.raw_ld + c) = o;
-            }
-            if (p.out_act) {
-              const float4 s2a = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
-              const float4 s2b = __ldg(reinterpret_cast<const float4*>(p.scale2 + c + 4));
-              const float4 h2a = __ldg(reinterpret_cast<const float4*>(p.shift2 + c));
-              const float4 h2b = __ldg(reinterpret_cast<const float4*>(p.shift2 + c + 4));
-              const float s2[8] = {s2a.x, s2a.y, s2a.z, s2a.w, s2b.x, s2b.y, s2b.z, s2b.w};
-              const float h2[8] = {h2a.x, h2a.y, h2a.z, h2a.w, h2b.x, h2b.y, h2b.z, h2b.w};
-              float w[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[e] = fmaxf(fmaf(bf16_round(v[e]), s2[e], h2[e]), 0.0f);
-              uint4 o;
-              o.x = pack_bf16x2(w[0], w[1]);
-              o.y = pack_bf16x2(w[2], w[3]);
-              o.z = pack_bf16x2(w[4], w[5]);
-              o.w = pack_bf16x2(w[6], w[7]);
-              *reinterpret_cast<uint4*>(p.out_act + pix * p.act_ld + c) = o;
+          }
+          if (has_res) {  // residual slab consumed: hand the slot back to its producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rempty_bar(rslot));
+            if (++rslot == (uint32_t)n_res) {
+              rslot = 0;
+              rphase ^= 1u;
             }
           }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA store
+          named_bar_sync(1, kEpiThreads);
+          if (leader) {
+            const int c0 = nt * BN + sl * 64;
+            if (has_raw) tma_store_4d(&p.tmRaw, raw_base + obuf * kSlabBytes, c0, x0, y0, n0);
+            if (has_act) tma_store_4d(&p.tmAct, act_base + obuf * kSlabBytes, c0, x0, y0, n0);
+            tma_store_commit();
+            tma_store_wait_read<1>();          // the other output buffer is no longer being read
+          }
+          named_bar_sync(2, kEpiThreads);
+          obuf ^= 1u;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    if (leader) tma_store_wait_read<0>();      // shared memory must outlive the last bulk store
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -277,22 +366,41 @@ int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int CoutPad, int BN
 }
 
 int conv_gemm_configure() {
-  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
-  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
-  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
-  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<256>::kSmemBytes));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   return DF3D_OK;
 }
 
-int launch_conv_gemm(const ConvParams& p, int BN, int num_sms, cudaStream_t stream) {
+int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t stream) {
+  ConvParams p = p_in;
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles_n;
   if (total <= 0) return DF3D_OK;
+  DF3D_REQUIRE(p.n_tiles_n * BN <= 256, DF3D_EUNSUPPORTED, "launch_conv_gemm: more than 256 output channels");
+  DF3D_REQUIRE(!(p.out_f32 && (p.out_raw || p.out_act || p.residual)), DF3D_EUNSUPPORTED,
+               "launch_conv_gemm: the fp32 output path takes no residual / bf16 outputs");
+  DF3D_REQUIRE(p.out_f32 || BN >= 64, DF3D_EUNSUPPORTED, "launch_conv_gemm: bf16 outputs need BN >= 64");
+  // shared-memory budget -> ring depths
+  const int stage_bytes = kABytes + BN * 128;
+  const int fixed = 1024 + kAffBytes + kBarBytes + (p.out_raw ? 2 * kSlabBytes : 0) + (p.out_act ? 2 * kSlabBytes : 0);
+  int n_res = p.residual ? kMaxResSlots : 0;
+  int n_stages = 0;
+  for (;; --n_res) {
+    n_stages = (kSmemLimit - fixed - n_res * kSlabBytes) / stage_bytes;
+    if (n_stages >= 2 || n_res <= (p.residual ? 1 : 0)) break;
+  }
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  DF3D_REQUIRE(n_stages >= 2, DF3D_EUNSUPPORTED, "launch_conv_gemm: shared-memory budget too small for BN=%d", BN);
+  p.n_stages = n_stages;
+  p.n_res_slots = n_res;
+  const int smem = n_stages * stage_bytes + n_res * kSlabBytes + fixed;
   const int grid = total < num_sms ? total : num_sms;
   switch (BN) {
-    case 32: conv_gemm_kernel<32><<<grid, kConvThreads, ConvCfg<32>::kSmemBytes, stream>>>(p); break;
-    case 64: conv_gemm_kernel<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, stream>>>(p); break;
-    case 128: conv_gemm_kernel<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, stream>>>(p); break;
-    case 256: conv_gemm_kernel<256><<<grid, kConvThreads, ConvCfg<256>::kSmemBytes, stream>>>(p); break;
+    case 32: conv_gemm_kernel<32><<<grid, kConvThreads, smem, stream>>>(p); break;
+    case 64: conv_gemm_kernel<64><<<grid, kConvThreads, smem, stream>>>(p); break;
+    case 128: conv_gemm_kernel<128><<<grid, kConvThreads, smem, stream>>>(p); break;
+    case 256: conv_gemm_kernel<256><<<grid, kConvThreads, smem, stream>>>(p); break;
     default: DF3D_REQUIRE(false, DF3D_EUNSUPPORTED, "launch_conv_gemm: BN=%d not instantiated", BN);
   }
   DF3D_LAUNCH_CHECK("conv_gemm_kernel");

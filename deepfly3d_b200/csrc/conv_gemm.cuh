@@ -12,8 +12,13 @@
 namespace df3d {
 
 struct ConvParams {
-  CUtensorMap tmA;  // activations, 4-D (C, W, H, N), box (64, tw, th, nb), SWIZZLE_128B, OOB = 0
-  CUtensorMap tmB;  // weights, 2-D (K, CoutPad) K-major, box (64, BN), SWIZZLE_128B
+  CUtensorMap tmA;    // activations, 4-D (C, W, H, N), box (64, tw, th, nb), SWIZZLE_128B, OOB = 0
+  CUtensorMap tmB;    // weights, 2-D (K, CoutPad) K-major, box (64, BN), SWIZZLE_128B
+  CUtensorMap tmRes;  // residual / out_raw / out_act: same 4-D box as tmA, one 64-channel slab per
+  CUtensorMap tmRaw;  // TMA load (residual) or TMA store (outputs)
+  CUtensorMap tmAct;
+  int n_stages;       // A/B ring depth (filled by launch_conv_gemm from the shared-memory budget)
+  int n_res_slots;    // residual ring depth (0 without residual)
   int taps;         // 1 (1x1) or 9 (3x3)
   int kc_per_tap;   // CinPad / 64
   int H, W, B;      // spatial size and number of images of this launch

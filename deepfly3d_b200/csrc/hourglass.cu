@@ -353,16 +353,19 @@ struct Emitter {
     if (residual && residual->valid) {
       p.residual = reinterpret_cast<const __nv_bfloat16*>(ptr(*residual));
       p.res_ld = residual->C;
+      if ((err = make_tmap_act(&p.tmRes, ptr(*residual), residual->C, in.W, in.H, B, tw, th, nb))) return;
     }
     if (out_raw && out_raw->valid) {
       p.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*out_raw));
       p.raw_ld = out_raw->C;
+      if ((err = make_tmap_act(&p.tmRaw, ptr(*out_raw), out_raw->C, in.W, in.H, B, tw, th, nb))) return;
     }
     if (out_act && out_act->valid && a2) {
       p.out_act = reinterpret_cast<__nv_bfloat16*>(ptr(*out_act));
       p.act_ld = out_act->C;
       p.scale2 = hg->d_a + a2->scale_off;
       p.shift2 = hg->d_a + a2->shift_off;
+      if ((err = make_tmap_act(&p.tmAct, ptr(*out_act), out_act->C, in.W, in.H, B, tw, th, nb))) return;
     }
     if (out_f32 && out_f32->valid) {
       p.out_f32 = reinterpret_cast<float*>(ptr(*out_f32));

@@ -190,7 +190,7 @@ int df3d_hg_set_mean(df3d_hg* hg, float m0, float m1, float m2);
  * the parity tests to check every layer shape against a float32 reference).  Stride 1, "same"
  * padding.  Packs the weights on every call (cudaMalloc + synchronous copy): NOT a hot-path call.
  *   in_dev (B,H,W,Cin) bf16 NHWC, Cin % 64 == 0;  w_host (Cout,Cin,k,k) float32, k in {1,3};
- *   Cout in {32,64,128,256};  v = conv*scale1[c] + shift1[c] (+ residual) ; relu1 ;
+ *   Cout in {64,128,256};  v = conv*scale1[c] + shift1[c] (+ residual) ; relu1 ;
  *   out_dev = bf16(v) ; out_act_dev = bf16(relu(bf16(v)*scale2[c] + shift2[c])) (optional). */
 int df3d_conv2d_nhwc_bf16(const void* in_dev, int B, int H, int W, int Cin, const float* w_host, int Cout,
                           int ksize, const float* scale1_host, const float* shift1_host, int relu1,

@@ -34,7 +34,7 @@ CASES = [
     (3, 4, 4, 256, 128, 1),
     (1, 128, 128, 64, 64, 3),
     (1, 128, 128, 64, 128, 1),
-    (2, 64, 64, 256, 32, 1),     # score head (N = 32)
+    (2, 64, 64, 256, 64, 1),     # intermediate score head (N = 64)
     (2, 64, 64, 64, 256, 1),     # score re-injection
     (1, 64, 128, 128, 128, 3),   # non-square map (reference heat-map 64 x 128)
     (1, 128, 128, 192, 64, 1),   # stem GEMM shape (K = 192)
