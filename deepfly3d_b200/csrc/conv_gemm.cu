@@ -27,6 +27,7 @@ constexpr int kEpiThreads = 128;
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // 128 rows x 64 bf16
 constexpr int kSlabBytes = kTileM * 128;  // one 64-channel bf16 slab of an output / residual tile
+constexpr int kHalfSlabBytes = kSlabBytes / 4;  // same slab at half resolution (32 pixels)
 constexpr int kMaxStages = 8;
 constexpr int kMaxResSlots = 4;
 constexpr int kAffBytes = 4 * 256 * 4;  // scale1, shift1, scale2, shift2 for up to 256 channels
@@ -50,9 +51,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle: 1024-byte aligned tiles
   const int n_stages = p.n_stages, n_res = p.n_res_slots;
   const bool has_res = n_res > 0, has_raw = p.out_raw != nullptr, has_act = p.out_act != nullptr;
+  const bool has_res2 = has_res && p.has_res2 != 0;
+  const uint32_t res_slot_bytes = kSlabBytes + (has_res2 ? kHalfSlabBytes : 0);
   // carve-up: [A/B ring][residual ring][raw out x2][act out x2][affine][barriers]
   const uint32_t res_base = smem_base + n_stages * kStageBytes;
-  const uint32_t raw_base = res_base + n_res * kSlabBytes;
+  const uint32_t raw_base = res_base + n_res * res_slot_bytes;
   const uint32_t act_base = raw_base + (has_raw ? 2 * kSlabBytes : 0);
   const uint32_t aff_base = act_base + (has_act ? 2 * kSlabBytes : 0);
   const uint32_t bar_base = aff_base + kAffBytes;
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     prefetch_tensormap(&p.tmA);
     prefetch_tensormap(&p.tmB);
     if (has_res) prefetch_tensormap(&p.tmRes);
+    if (has_res2) prefetch_tensormap(&p.tmRes2);
     if (has_raw) prefetch_tensormap(&p.tmRaw);
     if (has_act) prefetch_tensormap(&p.tmAct);
     for (int s = 0; s < n_stages; ++s) {
@@ -186,8 +190,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         decode_tile(tile, nt, x0, y0, n0);
         for (int sl = 0; sl < kSlabs; ++sl) {
           mbar_wait(rempty_bar(slot), phase ^ 1u);
-          mbar_arrive_expect_tx(rfull_bar(slot), kSlabBytes);
-          tma_load_4d(res_base + slot * kSlabBytes, &p.tmRes, rfull_bar(slot), nt * BN + sl * 64, x0, y0, n0);
+          mbar_arrive_expect_tx(rfull_bar(slot), res_slot_bytes);
+          tma_load_4d(res_base + slot * res_slot_bytes, &p.tmRes, rfull_bar(slot), nt * BN + sl * 64, x0, y0, n0);
+          if (has_res2)
+            tma_load_4d(res_base + slot * res_slot_bytes + kSlabBytes, &p.tmRes2, rfull_bar(slot), nt * BN + sl * 64,
+                        x0 >> 1, y0 >> 1, n0);
           if (++slot == (uint32_t)n_res) {
             slot = 0;
             phase ^= 1u;
@@ -202,6 +209,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const bool leader = (warp == kEpiWarp0) && (lane == 0);
     const uint32_t row_off = (uint32_t)m * 128u;
     const uint32_t sw = (uint32_t)(m & 7);
+    // row of this pixel's parent in the half-resolution residual slab (box tw/2 x th/2 x nb)
+    uint32_t row2_off = 0, sw2 = 0;
+    if (has_res2) {
+      const int w = m % p.tw, h = (m / p.tw) % p.th, nl = m / (p.tw * p.th);
+      const int r2 = (nl * (p.th >> 1) + (h >> 1)) * (p.tw >> 1) + (w >> 1);
+      row2_off = (uint32_t)r2 * 128u;
+      sw2 = (uint32_t)(r2 & 7);
+    }
     uint32_t it = 0, rslot = 0, rphase = 0, obuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
@@ -235,7 +250,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll 1
         for (int sl = 0; sl < kSlabs; ++sl) {
           if (has_res) mbar_wait(rfull_bar(rslot), rphase);
-          const uint32_t rbuf = res_base + rslot * kSlabBytes + row_off;
+          const uint32_t rbuf = res_base + rslot * res_slot_bytes + row_off;
+          const uint32_t rbuf2 = res_base + rslot * res_slot_bytes + kSlabBytes + row2_off;
           const uint32_t raw_buf = raw_base + obuf * kSlabBytes + row_off;
           const uint32_t act_buf = act_base + obuf * kSlabBytes + row_off;
 #pragma unroll
@@ -259,6 +275,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                   const float2 f = __bfloat1622float2(rh[e]);
                   v[2 * e] += f.x;
                   v[2 * e + 1] += f.y;
+                }
+              }
+              if (has_res2) {  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
+                const uint4 rr = lds128(rbuf2 + (((uint32_t)(half * 4 + j) ^ sw2) << 4));
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(rh[e]);
+                  v[2 * e] = bf16_round(v[2 * e]) + f.x;
+                  v[2 * e + 1] = bf16_round(v[2 * e + 1]) + f.y;
                 }
               }
               if (p.relu1) {
@@ -351,6 +377,21 @@ int make_tmap_act(CUtensorMap* out, const void* base, int C, int W, int H, int N
   return DF3D_OK;
 }
 
+int make_tmap_box(CUtensorMap* out, const void* base, int C, int W, int H, int N, int bw, int bh, int bn) {
+  if (int e = tma_init()) return e;
+  DF3D_REQUIRE(C % 64 == 0 && bw >= 1 && bh >= 1 && bn >= 1 && bw <= 256 && bh <= 256 && bn <= 256, DF3D_EINVAL,
+               "make_tmap_box: bad box %dx%dx%d", bw, bh, bn);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DF3D_REQUIRE(r == CUDA_SUCCESS, DF3D_ECUDA, "cuTensorMapEncodeTiled(box C=%d W=%d H=%d N=%d) failed: %d", C, W, H, N, (int)r);
+  return DF3D_OK;
+}
+
 int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int CoutPad, int BN) {
   if (int e = tma_init()) return e;
   DF3D_REQUIRE(K % 64 == 0 && CoutPad % BN == 0 && BN <= 256, DF3D_EINVAL, "make_tmap_wgt: bad shape K=%d Cout=%d BN=%d", K, CoutPad, BN);
@@ -384,17 +425,20 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
   // shared-memory budget -> ring depths
   const int stage_bytes = kABytes + BN * 128;
   const int fixed = 1024 + kAffBytes + kBarBytes + (p.out_raw ? 2 * kSlabBytes : 0) + (p.out_act ? 2 * kSlabBytes : 0);
+  DF3D_REQUIRE(!p.has_res2 || (p.residual && p.tw % 2 == 0 && p.th % 2 == 0), DF3D_EUNSUPPORTED,
+               "launch_conv_gemm: the half-resolution residual needs a full-resolution residual and an even tile");
+  const int res_slot = kSlabBytes + (p.has_res2 ? kHalfSlabBytes : 0);
   int n_res = p.residual ? kMaxResSlots : 0;
   int n_stages = 0;
   for (;; --n_res) {
-    n_stages = (kSmemLimit - fixed - n_res * kSlabBytes) / stage_bytes;
+    n_stages = (kSmemLimit - fixed - n_res * res_slot) / stage_bytes;
     if (n_stages >= 2 || n_res <= (p.residual ? 1 : 0)) break;
   }
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   DF3D_REQUIRE(n_stages >= 2, DF3D_EUNSUPPORTED, "launch_conv_gemm: shared-memory budget too small for BN=%d", BN);
   p.n_stages = n_stages;
   p.n_res_slots = n_res;
-  const int smem = n_stages * stage_bytes + n_res * kSlabBytes + fixed;
+  const int smem = n_stages * stage_bytes + n_res * res_slot + fixed;
   const int grid = total < num_sms ? total : num_sms;
   switch (BN) {
     case 32: conv_gemm_kernel<32><<<grid, kConvThreads, smem, stream>>>(p); break;

@@ -17,6 +17,9 @@ struct ConvParams {
   CUtensorMap tmRes;  // residual / out_raw / out_act: same 4-D box as tmA, one 64-channel slab per
   CUtensorMap tmRaw;  // TMA load (residual) or TMA store (outputs)
   CUtensorMap tmAct;
+  CUtensorMap tmRes2; // optional second residual at HALF resolution (nearest x2 up-sampled in the
+                      // epilogue): box (64, tw/2, th/2, nb) of the (C, W/2, H/2, N) tensor
+  int has_res2;
   int n_stages;       // A/B ring depth (filled by launch_conv_gemm from the shared-memory budget)
   int n_res_slots;    // residual ring depth (0 without residual)
   int taps;         // 1 (1x1) or 9 (3x3)
@@ -42,6 +45,8 @@ struct ConvParams {
 // host side ------------------------------------------------------------------------------------
 int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no libcuda link dependency)
 int make_tmap_act(CUtensorMap* out, const void* base, int C, int W, int H, int N, int tw, int th, int nb);
+// same, but the box need not hold 128 pixels (half-resolution residual slabs)
+int make_tmap_box(CUtensorMap* out, const void* base, int C, int W, int H, int N, int bw, int bh, int bn);
 int make_tmap_wgt(CUtensorMap* out, const void* base, int K, int CoutPad, int BN);
 int launch_conv_gemm(const ConvParams& p, int BN, int num_sms, cudaStream_t stream);
 int conv_gemm_configure();  // cudaFuncSetAttribute for the dynamic shared memory of every instantiation

@@ -3,7 +3,7 @@
 //                  with the uint8 -> float normalisation and the left-right mirror of the
 //                  "flipped" cameras (reference df3d/core.py:179) fused into the gather
 //   maxpool_bn_relu      : 2x2/2 max-pool -> raw + relu(bn(raw)) for the next bottleneck
-//   upsample_add_bn_relu : up1 + nearest_x2(low3) -> raw + relu(bn(raw))
+// (the hourglass' nearest x2 up-sample + add lives in the conv epilogue, see conv_gemm.cu)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -50,43 +50,67 @@ __device__ __forceinline__ uint4 bn_relu8(const uint4& raw_bits, const float* __
 }
 
 constexpr int kStemK = 147, kStemKPad = 192;
+constexpr int kStemPix = 32;                      // output pixels of one row segment per CTA
+constexpr int kStemCols = 2 * kStemPix + 5;       // input columns feeding them (7-wide window, stride 2)
 
+// One CTA = 32 consecutive output pixels of one output row.  The 7 x 69 x 3 input window is staged
+// in shared memory once (normalised, mirrored, zero padded), then the 32 x 24 sixteen-byte chunks of
+// the patch matrix are written fully coalesced.
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const void* __restrict__ img, int dtype, const uint8_t* __restrict__ flip, int B, int H, int W,
                    float m0, float m1, float m2, __nv_bfloat16* __restrict__ out) {
+  __shared__ float win[3][7][kStemCols + 1];
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)B * Ho * Wo * (kStemKPad / 8);
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  const int chunk = (int)(g % (kStemKPad / 8));
-  long long pixel = g / (kStemKPad / 8);
-  const int ox = (int)(pixel % Wo);
-  const int oy = (int)((pixel / Wo) % Ho);
-  const int b = (int)(pixel / ((long long)Wo * Ho));
+  const int segs = Wo / kStemPix;
+  int blk = blockIdx.x;
+  const int seg = blk % segs;
+  blk /= segs;
+  const int oy = blk % Ho;
+  const int b = blk / Ho;
+  const int ox0 = seg * kStemPix;
   const bool fl = flip ? (flip[b] != 0) : false;
   const float mean[3] = {m0, m1, m2};
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = chunk * 8 + e;
-    float val = 0.0f;
-    if (k < kStemK) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int ky = tap / 7, kx = tap - ky * 7;
-      const int iy = 2 * oy + ky - 3;
-      int ix = 2 * ox + kx - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        if (fl) ix = W - 1 - ix;
-        if (dtype == 0) {
-          val = (float)static_cast<const uint8_t*>(img)[((size_t)b * H + iy) * W + ix] / 255.0f - mean[c];
-        } else {
-          val = static_cast<const float*>(img)[(((size_t)b * 3 + c) * H + iy) * W + ix];
-        }
+  for (int i = threadIdx.x; i < 7 * kStemCols; i += 256) {
+    const int ky = i / kStemCols, cx = i - ky * kStemCols;
+    const int iy = 2 * oy + ky - 3;
+    int ix = 2 * ox0 + cx - 3;
+    float v[3] = {0.0f, 0.0f, 0.0f};
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (fl) ix = W - 1 - ix;
+      if (dtype == 0) {
+        const float g = (float)static_cast<const uint8_t*>(img)[((size_t)b * H + iy) * W + ix] / 255.0f;
+        v[0] = g - mean[0];
+        v[1] = g - mean[1];
+        v[2] = g - mean[2];
+      } else {
+        const float* f = static_cast<const float*>(img) + (size_t)b * 3 * H * W + (size_t)iy * W + ix;
+        v[0] = f[0];
+        v[1] = f[(size_t)H * W];
+        v[2] = f[(size_t)2 * H * W];
       }
     }
-    v[e] = val;
+    win[0][ky][cx] = v[0];
+    win[1][ky][cx] = v[1];
+    win[2][ky][cx] = v[2];
   }
-  *reinterpret_cast<uint4*>(out + (size_t)pixel * kStemKPad + chunk * 8) = pack8(v);
+  __syncthreads();
+  __nv_bfloat16* row = out + (((size_t)b * Ho + oy) * Wo + ox0) * kStemKPad;
+  for (int i = threadIdx.x; i < kStemPix * (kStemKPad / 8); i += 256) {
+    const int px = i / (kStemKPad / 8), chunk = i - px * (kStemKPad / 8);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = chunk * 8 + e;
+      float val = 0.0f;
+      if (k < kStemK) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        val = win[c][ky][2 * px + kx];
+      }
+      v[e] = val;
+    }
+    *reinterpret_cast<uint4*>(row + (size_t)i * 8) = pack8(v);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -123,38 +147,15 @@ maxpool_bn_relu_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W
   if (out_act) *reinterpret_cast<uint4*>(out_act + off) = bn_relu8(mx, scale, shift, c);
 }
 
-__global__ void __launch_bounds__(256)
-upsample_add_bn_relu_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low, int B, int H,
-                            int W, int C, const float* __restrict__ scale, const float* __restrict__ shift,
-                            __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act) {
-  const int C8 = C / 8;
-  const long long total = (long long)B * H * W * C8;
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  const int c = (int)(g % C8) * 8;
-  long long pixel = g / C8;
-  const int x = (int)(pixel % W);
-  const int y = (int)((pixel / W) % H);
-  const int b = (int)(pixel / ((long long)W * H));
-  const size_t off = (size_t)pixel * C + c;
-  const size_t loff = (((size_t)b * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c;
-  float a[8], l[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(up1 + off)), a);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(low + loff)), l);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) a[e] += l[e];
-  const uint4 raw = pack8(a);
-  *reinterpret_cast<uint4*>(out_raw + off) = raw;
-  if (out_act) *reinterpret_cast<uint4*>(out_act + off) = bn_relu8(raw, scale, shift, c);
-}
-
 static unsigned grid_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 int launch_stem_im2col(const void* img, int dtype, const uint8_t* flip, int B, int H, int W, const float mean[3],
                        __nv_bfloat16* out, cudaStream_t s) {
-  const long long total = (long long)B * (H / 2) * (W / 2) * (kStemKPad / 8);
-  if (total == 0) return DF3D_OK;
-  stem_im2col_kernel<<<grid_for(total), 256, 0, s>>>(img, dtype, flip, B, H, W, mean[0], mean[1], mean[2], out);
+  if (B == 0) return DF3D_OK;
+  DF3D_REQUIRE((W / 2) % kStemPix == 0, DF3D_EUNSUPPORTED, "stem_im2col: input width must be a multiple of %d", 2 * kStemPix);
+  const long long blocks = (long long)B * (H / 2) * ((W / 2) / kStemPix);
+  DF3D_REQUIRE(blocks < (1ll << 31), DF3D_EUNSUPPORTED, "stem_im2col: too many blocks");
+  stem_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(img, dtype, flip, B, H, W, mean[0], mean[1], mean[2], out);
   DF3D_LAUNCH_CHECK("stem_im2col_kernel");
   return DF3D_OK;
 }
@@ -165,16 +166,6 @@ int launch_maxpool_bn_relu(const __nv_bfloat16* in, int B, int H, int W, int C, 
   if (total == 0) return DF3D_OK;
   maxpool_bn_relu_kernel<<<grid_for(total), 256, 0, s>>>(in, B, H, W, C, scale, shift, out_raw, out_act);
   DF3D_LAUNCH_CHECK("maxpool_bn_relu_kernel");
-  return DF3D_OK;
-}
-
-int launch_upsample_add_bn_relu(const __nv_bfloat16* up1, const __nv_bfloat16* low, int B, int H, int W, int C,
-                                const float* scale, const float* shift, __nv_bfloat16* out_raw,
-                                __nv_bfloat16* out_act, cudaStream_t s) {
-  const long long total = (long long)B * H * W * (C / 8);
-  if (total == 0) return DF3D_OK;
-  upsample_add_bn_relu_kernel<<<grid_for(total), 256, 0, s>>>(up1, low, B, H, W, C, scale, shift, out_raw, out_act);
-  DF3D_LAUNCH_CHECK("upsample_add_bn_relu_kernel");
   return DF3D_OK;
 }
 

@@ -12,8 +12,5 @@ int launch_stem_im2col(const void* img, int dtype, const uint8_t* flip, int B, i
                        __nv_bfloat16* out, cudaStream_t s);
 int launch_maxpool_bn_relu(const __nv_bfloat16* in, int B, int H, int W, int C, const float* scale, const float* shift,
                            __nv_bfloat16* out_raw, __nv_bfloat16* out_act, cudaStream_t s);
-int launch_upsample_add_bn_relu(const __nv_bfloat16* up1, const __nv_bfloat16* low, int B, int H, int W, int C,
-                                const float* scale, const float* shift, __nv_bfloat16* out_raw,
-                                __nv_bfloat16* out_act, cudaStream_t s);
 
 }  // namespace df3d

@@ -5,10 +5,10 @@
 // df3d_hg_create parses the float32 parameter blob, folds every BatchNorm into a per-channel
 // (scale, shift) pair, packs every conv weight to bf16 [CoutPad][taps*CinPad] (K-major) and
 // uploads both once.  The forward is a fixed list of launches over a chunk of images:
-//   stem_im2col -> conv_gemm (tcgen05) x N, maxpool_bn_relu, upsample_add_bn_relu -> argmax.
+//   stem_im2col -> conv_gemm (tcgen05) x N, maxpool_bn_relu -> argmax.
 // Each conv's epilogue applies the *next* BatchNorm + ReLU (pre-activation bottlenecks), the
-// residual add and the bf16 rounding, so a bottleneck is exactly three (four with a projection)
-// GEMM launches and no elementwise pass.  All activations live in the caller's workspace; a
+// residual add, the hourglass' nearest x2 up-sample + add and the bf16 rounding, so a bottleneck is
+// exactly three (four with a projection) GEMM launches and no elementwise pass.  All activations live in the caller's workspace; a
 // small free-list arena reuses buffers so the working set stays small.
 #include <cmath>
 #include <cstdlib>
@@ -163,7 +163,7 @@ struct Arena {
   }
 };
 
-enum OpKind { OP_IM2COL, OP_CONV, OP_POOL, OP_UPADD, OP_ARGMAX };
+enum OpKind { OP_IM2COL, OP_CONV, OP_POOL, OP_ARGMAX };
 
 struct Op {
   OpKind kind;
@@ -195,6 +195,7 @@ struct df3d_hg {
   // host-side packed data (filled during the sizing pass)
   std::vector<uint16_t> wblob;
   std::vector<float> ablob;
+  std::vector<std::vector<float>> merged_w, merged_b;  // per-stack merged fc_/score_/score weights
   uint16_t* d_w = nullptr;
   float* d_a = nullptr;
   size_t ws_bytes = 0;
@@ -320,7 +321,7 @@ struct Emitter {
   // K = taps*CinPad.  Outputs may be invalid tensors (skipped).
   void conv(const Tensor& in, size_t w_off, int taps, int CinPad, int CoutPad, int BN, Affine a1, bool relu1,
             const Tensor* residual, const Tensor* out_raw, const Affine* a2, const Tensor* out_act,
-            const Tensor* out_f32, double flop_per_px) {
+            const Tensor* out_f32, double flop_per_px, const Tensor* res2_half = nullptr) {
     ++n_ops;
     if (err) return;
     if (dry) return;
@@ -355,6 +356,10 @@ struct Emitter {
       p.res_ld = residual->C;
       if ((err = make_tmap_act(&p.tmRes, ptr(*residual), residual->C, in.W, in.H, B, tw, th, nb))) return;
     }
+    if (res2_half && res2_half->valid) {
+      p.has_res2 = 1;
+      if ((err = make_tmap_box(&p.tmRes2, ptr(*res2_half), res2_half->C, in.W / 2, in.H / 2, B, tw / 2, th / 2, nb))) return;
+    }
     if (out_raw && out_raw->valid) {
       p.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*out_raw));
       p.raw_ld = out_raw->C;
@@ -374,11 +379,44 @@ struct Emitter {
     hg->ops.push_back(op);
   }
 
+  // merged inter-stack re-injection weights (see run()); cached on the handle so the views stay valid
+  Convp merged_skip(const StackP& s, int i) {
+    const int K = s.score.cout;
+    if ((int)hg->merged_w.size() <= i) {
+      hg->merged_w.resize(i + 1);
+      hg->merged_b.resize(i + 1);
+    }
+    std::vector<float>& W = hg->merged_w[i];
+    std::vector<float>& b = hg->merged_b[i];
+    if (W.empty()) {
+      W.assign((size_t)kCh * kCh, 0.0f);
+      b.assign(kCh, 0.0f);
+      for (int o = 0; o < kCh; ++o) {
+        double bb = (double)s.fc_.bias[o] + s.score_.bias[o];
+        for (int k = 0; k < K; ++k) bb += (double)s.score_.w[(size_t)o * K + k] * s.score.bias[k];
+        b[o] = (float)bb;
+        for (int c = 0; c < kCh; ++c) {
+          double acc = s.fc_.w[(size_t)o * kCh + c];
+          for (int k = 0; k < K; ++k) acc += (double)s.score_.w[(size_t)o * K + k] * s.score.w[(size_t)k * kCh + c];
+          W[(size_t)o * kCh + c] = (float)acc;
+        }
+      }
+    }
+    Convp m;
+    m.w = W.data();
+    m.bias = b.data();
+    m.cout = kCh;
+    m.cin = kCh;
+    m.k = 1;
+    return m;
+  }
+
   static int bn_for(int cout_pad) { return cout_pad >= 256 ? 256 : cout_pad; }
   static double fpp(const Convp& c) { return 2.0 * c.cin * c.cout * c.k * c.k; }
 
   // pre-activation bottleneck: x (raw) / xa = relu(bn1(x)) -> y (raw) [+ ya = relu(next_bn(y))]
-  void bottleneck(const Bott& b, const Tensor& x, const Tensor& xa, const BNp* next_bn, Tensor* y, Tensor* ya) {
+  void bottleneck(const Bott& b, const Tensor& x, const Tensor& xa, const BNp* next_bn, Tensor* y, Tensor* ya,
+                  const Tensor* up_add = nullptr) {
     const int H = x.H, W = x.W, P = b.planes, O = 2 * b.planes;
     // conv1 (1x1) with bn2+relu folded into its epilogue
     size_t w1 = pack_weights(b.c1, P, b.inpl);
@@ -412,7 +450,7 @@ struct Emitter {
     } else {
       *ya = Tensor();
     }
-    conv(t2, w3, 1, P, O, bn_for(O), a3, false, res, y, next_bn ? &an : nullptr, ya, nullptr, fpp(b.c3));
+    conv(t2, w3, 1, P, O, bn_for(O), a3, false, res, y, next_bn ? &an : nullptr, ya, nullptr, fpp(b.c3), up_add);
     tfree(t2);
     tfree(d);
   }
@@ -436,35 +474,19 @@ struct Emitter {
     hg->ops.push_back(op);
   }
 
-  void upadd(const Tensor& up1, const Tensor& low, const BNp& bn, Tensor* o, Tensor* oa) {
-    Affine a = bn_affine(bn, up1.C);
-    *o = talloc(up1.H, up1.W, up1.C);
-    *oa = talloc(up1.H, up1.W, up1.C);
-    ++n_ops;
-    if (dry || err) return;
-    Op op;
-    op.kind = OP_UPADD;
-    op.in0 = ptr(up1);
-    op.in1 = ptr(low);
-    op.out0 = ptr(*o);
-    op.out1 = ptr(*oa);
-    op.scale = hg->d_a + a.scale_off;
-    op.shift = hg->d_a + a.shift_off;
-    op.H = up1.H;
-    op.W = up1.W;
-    op.C = up1.C;
-    hg->ops.push_back(op);
-  }
-
-  // level n of the recursive hourglass of stack s; x/xa stay owned by the caller
+  // level n of the recursive hourglass of stack s; x/xa stay owned by the caller.
+  //   out = up1 + nearest_x2(low3),  up1 = hg[n-1][0](x),  low3 = hg[n-1][2](low2(hg[n-1][1](pool(x))))
+  // The low path runs first; the up-sample + add is folded into the epilogue of up1's last conv
+  // (second, half-resolution residual), so neither up1 nor a separate add pass touches HBM.
   void hourglass(const StackP& s, int n, const Tensor& x, const Tensor& xa, const BNp& out_bn, Tensor* o, Tensor* oa) {
-    Tensor up1, none;
-    bottleneck(s.hg[n - 1][0], x, xa, nullptr, &up1, &none);
+    Tensor none;
     Tensor p, pa;
     pool(x, s.hg[n - 1][1].bn1, &p, &pa);
     Tensor l1, l1a;
-    const BNp& low1_next = (n > 1) ? s.hg[n - 2][0].bn1 : s.hg[0][3].bn1;
-    bottleneck(s.hg[n - 1][1], p, pa, &low1_next, &l1, &l1a);
+    // low1 feeds (n > 1) the next level -- its pool takes the raw tensor, its up1 bottleneck the
+    // activated one -- or (n == 1) hg[0][3]
+    const BNp& low1_act_bn = (n > 1) ? s.hg[n - 2][0].bn1 : s.hg[0][3].bn1;
+    bottleneck(s.hg[n - 1][1], p, pa, &low1_act_bn, &l1, &l1a);
     tfree(p);
     tfree(pa);
     Tensor l2, l2a;
@@ -478,8 +500,7 @@ struct Emitter {
     bottleneck(s.hg[n - 1][2], l2, l2a, nullptr, &l3, &none);
     tfree(l2);
     tfree(l2a);
-    upadd(up1, l3, out_bn, o, oa);
-    tfree(up1);
+    bottleneck(s.hg[n - 1][0], x, xa, &out_bn, o, oa, &l3);
     tfree(l3);
   }
 
@@ -558,28 +579,22 @@ struct Emitter {
         tfree(x0);
         tfree(x0a);
       } else {
-        // intermediate score, kept as bf16 with 64 channels (rows >= K of the weights are zero)
-        size_t wsc = pack_weights(s.score, 64, kCh);
-        Affine as = conv_affine(s.score, nullptr, 64);
-        Tensor sc = talloc(H4, W4, 64);
-        conv(f, wsc, 1, kCh, 64, 64, as, false, nullptr, &sc, nullptr, nullptr, nullptr, fpp(s.score));
-        // u = fc_(f) + x
-        size_t wf_ = pack_weights(s.fc_, kCh, kCh);
-        Affine af_ = conv_affine(s.fc_, nullptr, kCh);
-        Tensor u = talloc(H4, W4, kCh);
-        conv(f, wf_, 1, kCh, kCh, 256, af_, false, &x0, &u, nullptr, nullptr, nullptr, fpp(s.fc_));
+        // x' = x + fc_(f) + score_(score(f)).  score is linear in f and nothing non-linear sits
+        // between score and score_, so the three convs collapse into ONE 256->256 conv with
+        //   W = W_fc_ + W_score_ @ W_score ,  b = b_fc_ + W_score_ @ b_score + b_score_
+        // (merged in fp32 on the host; the intermediate stacks' score maps are not an output).
+        Convp merged = merged_skip(s, i);
+        size_t wm = pack_weights(merged, kCh, kCh);
+        Affine am = conv_affine(merged, nullptr, kCh);
+        Affine an = bn_affine(net.stacks[i + 1].hg[kDepth - 1][0].bn1, kCh);
+        Tensor nx = talloc(H4, W4, kCh), nxa = talloc(H4, W4, kCh);
+        conv(f, wm, 1, kCh, kCh, 256, am, false, &x0, &nx, &an, &nxa, nullptr,
+             fpp(s.fc_) + fpp(s.score) + fpp(s.score_));
         tfree(f);
         tfree(x0);
         tfree(x0a);
-        // x' = score_(score) + u, and its activated copy for the next stack's first bottleneck
-        size_t ws_ = pack_weights(s.score_, kCh, 64);
-        Affine as_ = conv_affine(s.score_, nullptr, kCh);
-        Affine an = bn_affine(net.stacks[i + 1].hg[kDepth - 1][0].bn1, kCh);
-        x0 = talloc(H4, W4, kCh);
-        x0a = talloc(H4, W4, kCh);
-        conv(sc, ws_, 1, 64, kCh, 256, as_, false, &u, &x0, &an, &x0a, nullptr, fpp(s.score_));
-        tfree(u);
-        tfree(sc);
+        x0 = nx;
+        x0a = nxa;
       }
     }
     (void)K;
@@ -612,10 +627,11 @@ extern "C" size_t df3d_hg_param_count(const df3d_hg_desc* desc) {
 }
 
 static int chunk_for(const df3d_hg_desc& d) {
-  // images per launch sequence: enough tiles to fill 148 SMs on the coarse levels, small enough
-  // that the activations of one layer stay L2-friendly
+  // images per launch sequence.  Measured on B200 (profiles/): activations never fit the 126 MB L2
+  // at any useful chunk, and every launch costs ~10 us of fill/drain, so bigger is better; the cap
+  // keeps the workspace near 60 GB for 256x256 inputs.
   long long px = (long long)d.in_h * d.in_w;
-  int c = (int)((128ll * 256 * 256) / px);
+  int c = (int)((1792ll * 256 * 256) / px);
   if (c < 8) c = 8;
   if (const char* env = getenv("DF3D_HG_CHUNK")) {  // tuning / test knob: images per launch sequence
     const int v = atoi(env);
@@ -767,13 +783,6 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
                                              reinterpret_cast<__nv_bfloat16*>(op.out1), s))
             return e;
           break;
-        case OP_UPADD:
-          if (int e = launch_upsample_add_bn_relu(reinterpret_cast<const __nv_bfloat16*>(op.in0),
-                                                  reinterpret_cast<const __nv_bfloat16*>(op.in1), bc, op.H, op.W, op.C,
-                                                  op.scale, op.shift, reinterpret_cast<__nv_bfloat16*>(op.out0),
-                                                  reinterpret_cast<__nv_bfloat16*>(op.out1), s))
-            return e;
-          break;
         case OP_ARGMAX:
           if (int e = df3d_heatmap_argmax_nhwc(reinterpret_cast<const float*>(op.in0), bc, op.H, op.W, op.C, K,
                                                idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, stream))
@@ -862,16 +871,15 @@ extern "C" int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, doub
   if (op.kind == OP_CONV) {
     const ConvParams& p = op.conv;
     const double px = (double)p.H * p.W;
-    bpi = px * 2.0 * (p.kc_per_tap * 64 + (p.residual ? p.res_ld : 0) + (p.out_raw ? p.raw_ld : 0) + (p.out_act ? p.act_ld : 0)) +
+    bpi = px * 2.0 * (p.kc_per_tap * 64 + (p.residual ? p.res_ld : 0) + (p.has_res2 ? p.res_ld / 4.0 : 0) +
+                      (p.out_raw ? p.raw_ld : 0) + (p.out_act ? p.act_ld : 0)) +
           px * 4.0 * (p.out_f32 ? p.f32_ld : 0);
     snprintf(desc, desc_len, "conv%dx%d %4dx%-4d cin=%3d BN=%3d%s%s%s", p.taps == 9 ? 3 : 1, p.taps == 9 ? 3 : 1, p.H, p.W,
-             p.kc_per_tap * 64, op.BN, p.residual ? " +res" : "", p.out_act ? " +act" : "", p.out_f32 ? " f32" : "");
+             p.kc_per_tap * 64, op.BN, p.residual ? (p.has_res2 ? " +res+up" : " +res") : "", p.out_act ? " +act" : "",
+             p.out_f32 ? " f32" : "");
   } else if (op.kind == OP_POOL) {
     bpi = (double)op.H * op.W * op.C * 2.0 * 1.5;
     snprintf(desc, desc_len, "maxpool+bn  %4dx%-4d c=%3d", op.H, op.W, op.C);
-  } else if (op.kind == OP_UPADD) {
-    bpi = (double)op.H * op.W * op.C * 2.0 * 3.25;
-    snprintf(desc, desc_len, "upadd+bn    %4dx%-4d c=%3d", op.H, op.W, op.C);
   } else if (op.kind == OP_IM2COL) {
     bpi = (double)hg->desc.in_h * hg->desc.in_w + (double)hg->desc.in_h * hg->desc.in_w / 4 * kStemKPadCols * 2.0;
     snprintf(desc, desc_len, "stem im2col");

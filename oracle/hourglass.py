@@ -117,8 +117,17 @@ class HourglassNet(nn.Module):
             score = F.conv2d(y, wq(self.score[i]), self.score[i].bias)  # fp32, not rounded
             out.append(score)
             if i < self.num_stacks - 1:
-                u = rnd(F.conv2d(y, wq(self.fc_[i]), self.fc_[i].bias) + x)
-                x = rnd(F.conv2d(rnd(score), wq(self.score_[i]), self.score_[i].bias) + u)
+                if emulate_bf16:
+                    # the CUDA path merges the three linear maps x + fc_(y) + score_(score(y)) into
+                    # one 1x1 conv (weights merged in fp32/fp64, then rounded to bf16 once)
+                    Ws, bs = self.score[i].weight.double()[:, :, 0, 0], self.score[i].bias.double()
+                    Wr, br = self.score_[i].weight.double()[:, :, 0, 0], self.score_[i].bias.double()
+                    Wm = (self.fc_[i].weight.double()[:, :, 0, 0] + Wr @ Ws).float()
+                    bm = (self.fc_[i].bias.double() + Wr @ bs + br).float()
+                    x = rnd(F.conv2d(y, _bf16(Wm)[:, :, None, None], bm) + x)
+                else:
+                    x = x + F.conv2d(y, self.fc_[i].weight, self.fc_[i].bias) \
+                        + F.conv2d(score, self.score_[i].weight, self.score_[i].bias)
         return out
 
 
