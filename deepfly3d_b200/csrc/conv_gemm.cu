@@ -264,9 +264,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               const int c = nt * BN + sl * 64 + half * 32 + j * 8;
               const uint32_t chunk = ((uint32_t)(half * 4 + j) ^ sw) << 4;
               float v[8];
+              {
+                const uint4 sa = lds128(aff_base + 4u * c), sb = lds128(aff_base + 4u * c + 16u);
+                const uint4 ha = lds128(aff_base + 1024u + 4u * c), hb = lds128(aff_base + 1024u + 4u * c + 16u);
+                const uint32_t s1[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const uint32_t h1[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                v[e] = fmaf(__uint_as_float(r[j * 8 + e]), lds_f32(aff_base + 4u * (c + e)), lds_f32(aff_base + 1024u + 4u * (c + e)));
+                for (int e = 0; e < 8; ++e)
+                  v[e] = fmaf(__uint_as_float(r[j * 8 + e]), __uint_as_float(s1[e]), __uint_as_float(h1[e]));
+              }
               if (has_res) {
                 const uint4 rr = lds128(rbuf + chunk);
                 const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
@@ -301,9 +307,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
               if (has_act) {
                 float w[8];
+                const uint4 sa = lds128(aff_base + 2048u + 4u * c), sb = lds128(aff_base + 2048u + 4u * c + 16u);
+                const uint4 ha = lds128(aff_base + 3072u + 4u * c), hb = lds128(aff_base + 3072u + 4u * c + 16u);
+                const uint32_t s2[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const uint32_t h2[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                  w[e] = fmaxf(fmaf(bf16_round(v[e]), lds_f32(aff_base + 2048u + 4u * (c + e)), lds_f32(aff_base + 3072u + 4u * (c + e))), 0.0f);
+                  w[e] = fmaxf(fmaf(bf16_round(v[e]), __uint_as_float(s2[e]), __uint_as_float(h2[e])), 0.0f);
                 uint4 o;
                 o.x = pack_bf16x2(w[0], w[1]);
                 o.y = pack_bf16x2(w[2], w[3]);

@@ -188,8 +188,12 @@ using namespace df3d;
 struct df3d_hg {
   df3d_hg_desc desc;
   float mean[3] = {0.5f, 0.5f, 0.5f};
-  int chunk = 0;
+  int chunk = 0;     // images per lane and launch sequence
+  int n_lanes = 1;   // independent image groups run concurrently on their own stream and SM share
   int num_sms = 148;
+  size_t lane_bytes = 0;
+  cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused (caller's stream)
+  cudaEvent_t fork_ev = nullptr, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<float> params;  // host copy of the blob (views in `net` point into it)
   NetP net;
   // host-side packed data (filled during the sizing pass)
@@ -202,7 +206,8 @@ struct df3d_hg {
   int ops_per_chunk = 0;
   // plan for the workspace pointer it was built for
   char* plan_base = nullptr;
-  std::vector<Op> ops;
+  std::vector<Op> ops;            // plan under construction / lane 0 (all lanes share its structure)
+  std::vector<std::vector<Op>> lane_ops;
   char* heat_ptr = nullptr;  // fp32 score tensor of the last stack inside the workspace
   int Hh = 0, Wh = 0;
   // optional per-launch timing (bench / profiling only): events[chunk][op][2]
@@ -626,18 +631,33 @@ extern "C" size_t df3d_hg_param_count(const df3d_hg_desc* desc) {
   return param_count(*desc);
 }
 
-static int chunk_for(const df3d_hg_desc& d) {
-  // images per launch sequence.  Measured on B200 (profiles/): activations never fit the 126 MB L2
-  // at any useful chunk, and every launch costs ~10 us of fill/drain, so bigger is better; the cap
-  // keeps the workspace near 60 GB for 256x256 inputs.
+static int lanes_for(const df3d_hg_desc& d) {
+  // One lane by default.  DF3D_HG_LANES=n splits the batch over n streams with 1/n of the SMs each
+  // so that tensor-bound 3x3 convs of one lane could overlap HBM-bound 1x1 convs of another;
+  // measured on B200 (profiles/r01_lanes.txt) this is slower (242 / 281 / 330 ms for 1 / 2 / 3
+  // lanes at 1792 images), so it stays a tuning knob only.
+  (void)d;
+  int l = 1;
+  if (const char* env = getenv("DF3D_HG_LANES")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 4) l = v;
+  }
+  return l;
+}
+
+static int chunk_for(const df3d_hg_desc& d, int lanes) {
+  // images per lane and launch sequence.  Measured on B200 (profiles/): activations never fit the
+  // 126 MB L2 at any useful chunk, and every launch costs ~10 us of fill/drain, so bigger is
+  // better; the cap keeps the whole workspace near 60 GB for 256x256 inputs.
   long long px = (long long)d.in_h * d.in_w;
-  int c = (int)((1792ll * 256 * 256) / px);
+  int c = (int)((1792ll * 256 * 256) / px) / lanes;
   if (c < 8) c = 8;
-  if (const char* env = getenv("DF3D_HG_CHUNK")) {  // tuning / test knob: images per launch sequence
+  if (const char* env = getenv("DF3D_HG_CHUNK")) {  // tuning / test knob
     const int v = atoi(env);
     if (v >= 1) c = v;
   }
-  if (c > d.max_batch) c = d.max_batch;
+  const int need = (d.max_batch + lanes - 1) / lanes;
+  if (c > need) c = need;
   return c;
 }
 
@@ -645,14 +665,15 @@ extern "C" size_t df3d_hg_workspace_bytes(const df3d_hg_desc* desc) {
   if (check_desc(desc, "df3d_hg_workspace_bytes")) return 0;
   df3d_hg tmp;
   tmp.desc = *desc;
-  tmp.chunk = chunk_for(*desc);
+  tmp.n_lanes = lanes_for(*desc);
+  tmp.chunk = chunk_for(*desc, tmp.n_lanes);
   tmp.params.assign(param_count(*desc), 0.0f);
   Cursor c{tmp.params.data(), tmp.params.size()};
   read_net(c, desc->num_stacks, desc->num_classes, &tmp.net);
   Emitter e{&tmp, true, nullptr};
   e.B = tmp.chunk;
   e.run();
-  return e.arena.top + 1024;
+  return (size_t)tmp.n_lanes * ((e.arena.top + 1023) & ~size_t(1023)) + 1024;
 }
 
 extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host, size_t n_params, df3d_hg** out) {
@@ -672,7 +693,8 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
   df3d_hg* hg = new df3d_hg();
   hg->desc = *desc;
   hg->num_sms = prop.multiProcessorCount;
-  hg->chunk = chunk_for(*desc);
+  hg->n_lanes = lanes_for(*desc);
+  hg->chunk = chunk_for(*desc, hg->n_lanes);
   hg->params.assign(params_host, params_host + n_params);
   Cursor c{hg->params.data(), hg->params.size()};
   read_net(c, desc->num_stacks, desc->num_classes, &hg->net);
@@ -683,9 +705,15 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
   Emitter e{hg, true, nullptr};
   e.B = hg->chunk;
   e.run();
-  hg->ws_bytes = e.arena.top + 1024;
+  hg->lane_bytes = (e.arena.top + 1023) & ~size_t(1023);
+  hg->ws_bytes = (size_t)hg->n_lanes * hg->lane_bytes + 1024;
   hg->ops_per_chunk = e.n_ops;
   cudaError_t ce = cudaMalloc(&hg->d_w, hg->wblob.size() * sizeof(uint16_t));
+  if (ce == cudaSuccess && hg->n_lanes > 1) ce = cudaEventCreateWithFlags(&hg->fork_ev, cudaEventDisableTiming);
+  for (int l = 1; l < hg->n_lanes && ce == cudaSuccess; ++l) {
+    ce = cudaStreamCreateWithFlags(&hg->lane_stream[l], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&hg->join_ev[l], cudaEventDisableTiming);
+  }
   if (ce == cudaSuccess) ce = cudaMalloc(&hg->d_a, hg->ablob.size() * sizeof(float));
   if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_w, hg->wblob.data(), hg->wblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_a, hg->ablob.data(), hg->ablob.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -707,24 +735,55 @@ extern "C" void df3d_hg_destroy(df3d_hg* hg) {
   if (hg->d_w) cudaFree(hg->d_w);
   if (hg->d_a) cudaFree(hg->d_a);
   for (cudaEvent_t ev : hg->events) cudaEventDestroy(ev);
+  if (hg->fork_ev) cudaEventDestroy(hg->fork_ev);
+  for (int l = 1; l < 4; ++l) {
+    if (hg->join_ev[l]) cudaEventDestroy(hg->join_ev[l]);
+    if (hg->lane_stream[l]) cudaStreamDestroy(hg->lane_stream[l]);
+  }
   delete hg;
 }
 
 static int build_plan(df3d_hg* hg, char* base) {
-  hg->ops.clear();
-  hg->heat_ptr = nullptr;
-  Emitter e{hg, false, base};
-  e.B = hg->chunk;
-  e.run();
-  if (e.err) return e.err;
+  hg->lane_ops.assign(hg->n_lanes, std::vector<Op>());
+  for (int l = hg->n_lanes - 1; l >= 0; --l) {  // lane 0 last: hg->ops keeps its plan for the descriptions
+    hg->ops.clear();
+    hg->heat_ptr = nullptr;
+    Emitter e{hg, false, base + (size_t)l * hg->lane_bytes};
+    e.B = hg->chunk;
+    e.run();
+    if (e.err) return e.err;
+    hg->lane_ops[l] = hg->ops;
+  }
   hg->plan_base = base;
   return DF3D_OK;
 }
 
+// how a batch is cut: rounds of up to n_lanes * chunk images, split evenly over the lanes
+struct Piece {
+  int lane, c0, bc, active_lanes;
+};
+static std::vector<Piece> cut_batch(const df3d_hg* hg, int B) {
+  std::vector<Piece> out;
+  int pos = 0;
+  while (pos < B) {
+    const int round = (B - pos) < hg->n_lanes * hg->chunk ? (B - pos) : hg->n_lanes * hg->chunk;
+    const int per = (round + hg->n_lanes - 1) / hg->n_lanes;
+    int active = 0;
+    for (int l = 0; l < hg->n_lanes; ++l)
+      if (l * per < round) ++active;
+    for (int l = 0; l < active; ++l) {
+      const int c0 = pos + l * per;
+      const int bc = (pos + round - c0) < per ? (pos + round - c0) : per;
+      out.push_back(Piece{l, c0, bc, active});
+    }
+    pos += round;
+  }
+  return out;
+}
+
 extern "C" int df3d_hg_launches_per_forward(const df3d_hg* hg, int B) {
   if (!hg || B <= 0) return 0;
-  const int chunks = (B + hg->chunk - 1) / hg->chunk;
-  return hg->ops_per_chunk * chunks;
+  return hg->ops_per_chunk * (int)cut_batch(hg, B).size();
 }
 
 extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int dtype, const uint8_t* flip_dev,
@@ -737,7 +796,7 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
                workspace_bytes, hg->ws_bytes);
   if (B == 0) return DF3D_OK;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace_dev) + 1023) & ~uintptr_t(1023));
-  if (hg->plan_base != base || hg->ops.empty())
+  if (hg->plan_base != base || hg->lane_ops.empty())
     if (int e = build_plan(hg, base)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const df3d_hg_desc& d = hg->desc;
@@ -746,27 +805,34 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
   const size_t heat_elems = (size_t)hg->Hh * hg->Wh * kHeatPad;
 
   const size_t n_ops = hg->ops.size();
+  const std::vector<Piece> pieces = cut_batch(hg, B);
   if (hg->timing) {
-    const size_t chunks = (size_t)(B + hg->chunk - 1) / hg->chunk;
-    while (hg->events.size() < chunks * n_ops * 2) {
+    while (hg->events.size() < pieces.size() * n_ops * 2) {
       cudaEvent_t ev;
       DF3D_CUDA(cudaEventCreate(&ev));
       hg->events.push_back(ev);
     }
     hg->timed_bc.clear();
   }
-  for (int c0 = 0; c0 < B; c0 += hg->chunk) {
-    const int bc = (B - c0) < hg->chunk ? (B - c0) : hg->chunk;
+  for (size_t pi = 0; pi < pieces.size(); ++pi) {
+    const Piece& pc = pieces[pi];
+    const int c0 = pc.c0, bc = pc.bc;
+    // lane 0 runs on the caller's stream; the other lanes fork from it and join back
+    cudaStream_t ls = pc.lane == 0 ? s : hg->lane_stream[pc.lane];
+    if (pc.lane == 0 && pc.active_lanes > 1) DF3D_CUDA(cudaEventRecord(hg->fork_ev, s));
+    if (pc.lane > 0) DF3D_CUDA(cudaStreamWaitEvent(ls, hg->fork_ev, 0));
+    const int sms = pc.active_lanes > 1 ? hg->num_sms / pc.active_lanes : hg->num_sms;
+    const std::vector<Op>& ops = hg->lane_ops[pc.lane];
     const size_t ev_base = hg->timing ? hg->timed_bc.size() * n_ops * 2 : 0;
     if (hg->timing) hg->timed_bc.push_back(bc);
     for (size_t oi = 0; oi < n_ops; ++oi) {
-      const Op& op = hg->ops[oi];
-      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi], s));
+      const Op& op = ops[oi];
+      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi], ls));
       switch (op.kind) {
         case OP_IM2COL: {
           const char* img = static_cast<const char*>(images_dev) + (size_t)c0 * img_stride;
           if (int e = launch_stem_im2col(img, dtype, flip_dev ? flip_dev + c0 : nullptr, bc, d.in_h, d.in_w, hg->mean,
-                                         reinterpret_cast<__nv_bfloat16*>(op.out0), s))
+                                         reinterpret_cast<__nv_bfloat16*>(op.out0), ls))
             return e;
           break;
         }
@@ -774,25 +840,29 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
           ConvParams p = op.conv;
           p.B = bc;
           p.tiles_b = (bc + op.nb - 1) / op.nb;
-          if (int e = launch_conv_gemm(p, op.BN, hg->num_sms, s)) return e;
+          if (int e = launch_conv_gemm(p, op.BN, sms, ls)) return e;
           break;
         }
         case OP_POOL:
           if (int e = launch_maxpool_bn_relu(reinterpret_cast<const __nv_bfloat16*>(op.in0), bc, op.H, op.W, op.C, op.scale,
                                              op.shift, reinterpret_cast<__nv_bfloat16*>(op.out0),
-                                             reinterpret_cast<__nv_bfloat16*>(op.out1), s))
+                                             reinterpret_cast<__nv_bfloat16*>(op.out1), ls))
             return e;
           break;
         case OP_ARGMAX:
           if (int e = df3d_heatmap_argmax_nhwc(reinterpret_cast<const float*>(op.in0), bc, op.H, op.W, op.C, K,
-                                               idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, stream))
+                                               idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, ls))
             return e;
           if (heatmap_dev)
             DF3D_CUDA(cudaMemcpyAsync(heatmap_dev + (size_t)c0 * heat_elems, op.in0, (size_t)bc * heat_elems * sizeof(float),
-                                      cudaMemcpyDeviceToDevice, s));
+                                      cudaMemcpyDeviceToDevice, ls));
           break;
       }
-      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi + 1], s));
+      if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi + 1], ls));
+    }
+    if (pc.lane > 0) {
+      DF3D_CUDA(cudaEventRecord(hg->join_ev[pc.lane], ls));
+      DF3D_CUDA(cudaStreamWaitEvent(s, hg->join_ev[pc.lane], 0));
     }
   }
   return DF3D_OK;

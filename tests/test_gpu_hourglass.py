@@ -103,3 +103,11 @@ def test_batch_larger_than_chunk_is_consistent(hgmod, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(ia, ib) and torch.equal(ca, cb)
     assert eng_b.launches(11) == 3 * eng_a.launches(11)
+    # two concurrent lanes (own stream, half of the SMs each), ragged split 6 + 5 and 2+2 / 2+2 / 2+1
+    for chunk in ("8", "2"):
+        monkeypatch.setenv("DF3D_HG_LANES", "2")
+        monkeypatch.setenv("DF3D_HG_CHUNK", chunk)
+        eng_c = hgmod.HourglassEngine(model.state_dict(), 128, 128, max_batch=11)
+        ic, cc = eng_c.forward(img)
+        torch.cuda.synchronize()
+        assert torch.equal(ia, ic) and torch.equal(ca, cc)
