@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_RANK, help="frames per rank and step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="ncu helper: warm up, then run --steps resident steps inside the NVTX range 'df3d_step' and exit "
+                         "(no JSON line; numbers taken under a profiler are never bench values)")
     return ap.parse_args()
 
 
@@ -283,6 +286,14 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.profile:
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("df3d_step")
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
     ms_res, clocks, _ = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
     # separate pass with per-launch events for the roofline of the dominant kernel
     pipe.engine.set_timing(True)

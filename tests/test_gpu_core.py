@@ -63,8 +63,19 @@ def test_pose_estimation_matches_oracle(working):
         heat = model(x, emulate_bf16=True)[-1]
     idx, conf = oargmax.heatmap_argmax(heat.numpy())
     ref = opack.pack_points2d(opack.indices_to_points2d(idx.reshape(7, 3, 19), (64, 128)), range(7))
-    # structure is exact (zeros, (0,1) quirk, camera 3 dropped); coordinates within one heat-map cell
-    assert np.array_equal(core.points2d == 0, ref == 0) or np.abs(core.points2d - ref).max() <= 0.02
+    # the packing structure is exact: camera 3 dropped, camera 2 joints 15.., camera 4 joints 34.. blanked,
+    # unseen halves zero / (0, 1) after the un-flip (core.py:187-199)
+    blank = np.zeros((7, 3, 38), dtype=bool)
+    blank[3] = True
+    blank[:3, :, 19:] = True
+    blank[4:, :, :19] = True
+    blank[2, :, 15:] = True
+    blank[4, :, 34:] = True
+    assert np.array_equal(core.points2d[blank], ref[blank])
+    assert np.all(core.points2d[:4][blank[:4]] == 0) and np.all(core.points2d[4:][blank[4:]] == [0.0, 1.0])
+    # coordinates: the seeded random network has nearly flat score maps, so a bf16-level difference in
+    # the accumulation order moves some arg-maxes (tests/test_gpu_hourglass.py measures exactly that);
+    # the reference's own tolerance (atol 0.02, test_df3d.py:171) must hold for the bulk of the joints
     close = np.abs(core.points2d - ref).max(axis=-1) <= 0.02
     assert close.mean() > 0.8, f"only {close.mean():.3f} of the joints within atol 0.02 of the oracle"
     rngv = float(heat.max() - heat.min())

@@ -1,15 +1,25 @@
 #!/bin/bash
-# GPU session: full gpu test suite, smoke, bench, ncu launch list + one full capture of the top kernel
+# GPU session: full gpu test suite, smoke, bench, and (with "ncu") the ncu launch list of one bench
+# step + full captures of the dominant kernels.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 ( timeout -s KILL 900 python -m pytest tests -q -m gpu --no-header -rA -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" ) | tee gpurun_out/summary.txt
 ( timeout -s KILL 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" ) | tee -a gpurun_out/summary.txt
 ( timeout -s KILL 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit=$?" ) | tee -a gpurun_out/summary.txt
 tail -3 gpurun_out/bench.log
+( timeout -s KILL 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "bench ref exit=$?" ) | tee -a gpurun_out/summary.txt
+tail -1 gpurun_out/bench_ref.log
 if [ "$1" = "ncu" ]; then
-  timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 1 --warmup 0 --frames 32 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-  echo "ncu launches exit=$?" | tee -a gpurun_out/summary.txt
-  timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 40 -c 6 -o gpurun_out/prof_conv \
-      python bench.py --steps 1 --warmup 0 --frames 32 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-  echo "ncu full exit=$?" | tee -a gpurun_out/summary.txt
+  # launch list of ONE full-size bench step (NVTX range df3d_step; warm-up launches excluded)
+  timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
+  echo "ncu launches exit=$? lines=$(wc -l < gpurun_out/launches.csv)" | tee -a gpurun_out/summary.txt
+  # full captures (small batch: ncu replays each launch ~40x): a few conv launches of each shape class + the 2D->3D tail
+  timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --set full --clock-control none --import-source on \
+      -k regex:conv_gemm_kernel -s 4 -c 12 -f -o gpurun_out/prof_conv \
+      python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full conv exit=$?" | tee -a gpurun_out/summary.txt
+  timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --set full --clock-control none --import-source on \
+      -k regex:'argmax|pack_points|triangulate|ba_linearize|ba_solve|ba_evaluate|maxpool|im2col' -c 12 -f -o gpurun_out/prof_tail \
+      python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_tail.log 2>&1
+  echo "ncu full tail exit=$?" | tee -a gpurun_out/summary.txt
 fi
