@@ -1,0 +1,61 @@
+// Convolution *chains* for sm_100a: one implicit-GEMM conv (1x1 or 3x3, the "head") followed by up to
+// four point-wise (1x1) convs evaluated on the same 128-pixel tile without leaving the SM.
+//
+// Every hourglass bottleneck is  relu(bn) -> 1x1 -> relu(bn) -> 3x3 -> relu(bn) -> 1x1 (+ residual);
+// unfused, the 128/256-channel tensors between those convs make the 1x1 layers HBM-bound.  In a
+// chain, the epilogue of stage i turns its fp32 accumulator (TMEM) into the bf16 activation the next
+// conv consumes and stores it back into TMEM as the A operand of the next tcgen05.mma (A-from-TMEM
+// form), so only the tensors that other layers need (the residual stream, the next block's 3x3
+// input) are written to HBM.  Replaces the torch conv2d/batch_norm/relu/add calls of the hourglass
+// inside df2d (reference call site df3d/core.py:177-185).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace df3d {
+
+constexpr int kMaxChain = 5;
+
+struct ChainStage {
+  CUtensorMap tmB;     // weights, 2-D (K, N) K-major, box (64, 128), SWIZZLE_128B
+  CUtensorMap tmRes;   // residual added in this stage's epilogue: 4-D box (64, tw, th, nb)
+  CUtensorMap tmRes2;  // second residual at half resolution (nearest x2 up-sample + add)
+  // epilogue:  v = acc*scale1[c] + shift1[c] (+ residual) (+ up(residual2)) ; relu1 ;
+  //            raw = bf16(v) ; act = bf16(relu(raw*scale2[c] + shift2[c]))
+  const float* scale1;
+  const float* shift1;
+  const float* scale2;
+  const float* shift2;
+  __nv_bfloat16* out_raw;  // bf16 output of this stage, NHWC with `n` channels per pixel (256-bit stores), or null
+  int n;         // output channels: 128 or 256
+  int kblocks;   // K / 64 (head: taps * Cin/64; later stages: n of the previous stage / 64)
+  int relu1;
+  int has_res, has_res2;
+  int x_src;     // operand handed to the next stage: 0 none (last stage), 1 raw, 2 act
+  int acc_col;   // TMEM column of this stage's accumulator (filled by launch_conv_chain)
+  int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)
+};
+
+struct ChainParams {
+  CUtensorMap tmA;  // head activations, 4-D (C, W, H, N), box (64, tw, th, nb), SWIZZLE_128B, OOB = 0
+  ChainStage st[kMaxChain];
+  int n_chain;
+  int taps;        // head: 1 or 9
+  int kc_per_tap;  // head: Cin / 64
+  int H, W, B;
+  int tw, th, nb;  // M tile = nb images x th rows x tw cols = 128 pixels
+  int tiles_x, tiles_y, tiles_b;
+  // shared-memory carve-up (filled by launch_conv_chain)
+  int n_m;         // head ring (A tiles + head weights), 16 KB units
+  int n_w;         // weight ring of the later stages, 16 KB units
+  int n_slabs;     // residual slabs (TMA prefetch ring)
+  int slab_bytes;  // 16384 (+4096 with a half-resolution residual)
+  int aff_bytes;
+};
+
+int conv_chain_configure();
+int launch_conv_chain(const ChainParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace df3d

@@ -14,6 +14,8 @@
 //     prefetched by TMA) -> ReLU / bf16 rounding -> 128B-swizzled shared-memory slab -> TMA store.
 //     Every global access of the kernel is a TMA bulk transfer (fully coalesced, asynchronous); the
 //     only direct stores left are the fp32 score maps of the last stack.
+#include <cstdlib>
+
 #include "conv_gemm.cuh"
 #include "sm100.cuh"
 
@@ -445,6 +447,10 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
     if (n_stages >= 2 || n_res <= (p.residual ? 1 : 0)) break;
   }
   if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (const char* env = getenv("DF3D_CONV_STAGES")) {  // profiling knob: cap the ring depth
+    const int v = atoi(env);
+    if (v >= 2 && v < n_stages) n_stages = v;
+  }
   DF3D_REQUIRE(n_stages >= 2, DF3D_EUNSUPPORTED, "launch_conv_gemm: shared-memory budget too small for BN=%d", BN);
   p.n_stages = n_stages;
   p.n_res_slots = n_res;

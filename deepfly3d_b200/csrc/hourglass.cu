@@ -16,6 +16,7 @@
 #include <map>
 #include <vector>
 
+#include "conv_chain.cuh"
 #include "conv_gemm.cuh"
 #include "hg_elementwise.cuh"
 
@@ -163,12 +164,14 @@ struct Arena {
   }
 };
 
-enum OpKind { OP_IM2COL, OP_CONV, OP_POOL, OP_ARGMAX };
+enum OpKind { OP_IM2COL, OP_CONV, OP_CHAIN, OP_POOL, OP_ARGMAX };
 
 struct Op {
   OpKind kind;
-  // conv
+  // conv / chain
   ConvParams conv;
+  ChainParams chain;
+  double chain_bytes_per_image = 0.0;  // algorithmic HBM bytes of a chain (head input + residuals + stored outputs)
   int BN = 0, nb = 1;
   // elementwise / argmax: byte offsets resolved to pointers at plan time
   char *in0 = nullptr, *in1 = nullptr, *out0 = nullptr, *out1 = nullptr;
@@ -190,6 +193,7 @@ struct df3d_hg {
   float mean[3] = {0.5f, 0.5f, 0.5f};
   int chunk = 0;     // images per lane and launch sequence
   int n_lanes = 1;   // independent image groups run concurrently on their own stream and SM share
+  int fuse = 2;      // 0: one launch per conv, 1: point-wise chains behind stand-alone 3x3 convs, 2: 3x3-led chains
   int num_sms = 148;
   size_t lane_bytes = 0;
   cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused (caller's stream)
@@ -460,6 +464,309 @@ struct Emitter {
     tfree(d);
   }
 
+  // ------------------------------------------------------------------ fused plan (conv chains)
+  struct StageSpec {
+    size_t w_off = 0;
+    int K = 0, N = 0;  // packed weights [N][K]
+    Affine a1{};
+    bool relu1 = false;
+    const Tensor* residual = nullptr;
+    const Tensor* res2_half = nullptr;
+    const Tensor* out_raw = nullptr;
+    int x_src = 0;     // 0: last stage, 1: next stage takes bf16(v), 2: relu(bn(bf16(v))) with a2
+    Affine a2{};
+    double flop_per_px = 0.0;
+  };
+
+  // One chain launch: head conv (taps x CinPad from `in`) + point-wise stages on the same tiles.
+  void chain(const Tensor& in, int taps, int CinPad, const StageSpec* sp, int n) {
+    ++n_ops;
+    if (err || dry) return;
+    Op op;
+    op.kind = OP_CHAIN;
+    ChainParams& p = op.chain;
+    memset(&p, 0, sizeof(p));
+    int tw, th, nb;
+    tile_geometry(in.H, in.W, &tw, &th, &nb);
+    op.nb = nb;
+    if ((err = make_tmap_act(&p.tmA, ptr(in), in.C, in.W, in.H, B, tw, th, nb))) return;
+    p.n_chain = n;
+    p.taps = taps;
+    p.kc_per_tap = CinPad / 64;
+    p.H = in.H;
+    p.W = in.W;
+    p.B = B;
+    p.tw = tw;
+    p.th = th;
+    p.nb = nb;
+    p.tiles_x = in.W / tw;
+    p.tiles_y = in.H / th;
+    p.tiles_b = (B + nb - 1) / nb;
+    double bytes_px = 2.0 * in.C;
+    for (int i = 0; i < n; ++i) {
+      const StageSpec& s = sp[i];
+      ChainStage& st = p.st[i];
+      if ((err = make_tmap_wgt(&st.tmB, hg->d_w + s.w_off, s.K, s.N, 128))) return;
+      st.n = s.N;
+      st.kblocks = s.K / 64;
+      st.relu1 = s.relu1 ? 1 : 0;
+      st.scale1 = hg->d_a + s.a1.scale_off;
+      st.shift1 = hg->d_a + s.a1.shift_off;
+      st.x_src = s.x_src;
+      if (s.x_src == 2) {
+        st.scale2 = hg->d_a + s.a2.scale_off;
+        st.shift2 = hg->d_a + s.a2.shift_off;
+      }
+      if (s.residual && s.residual->valid) {
+        st.has_res = 1;
+        if ((err = make_tmap_act(&st.tmRes, ptr(*s.residual), s.residual->C, in.W, in.H, B, tw, th, nb))) return;
+        bytes_px += 2.0 * s.N;
+      }
+      if (s.res2_half && s.res2_half->valid) {
+        st.has_res2 = 1;
+        if ((err = make_tmap_box(&st.tmRes2, ptr(*s.res2_half), s.res2_half->C, in.W / 2, in.H / 2, B, tw / 2, th / 2, nb))) return;
+        bytes_px += 0.5 * s.N;
+      }
+      if (s.out_raw && s.out_raw->valid) {
+        if (s.out_raw->C != s.N) {
+          err = DF3D_EINVAL;
+          set_error("chain: stage %d stores %d channels into a %d-channel tensor", i, s.N, s.out_raw->C);
+          return;
+        }
+        st.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*s.out_raw));
+        bytes_px += 2.0 * s.N;
+      }
+      op.flops_per_image += s.flop_per_px * in.H * in.W;
+    }
+    op.chain_bytes_per_image = bytes_px * in.H * in.W;
+    hg->ops.push_back(op);
+  }
+
+  // stand-alone conv1 of a bottleneck (input already activated): t1 = relu(bn2(conv1(xa)))
+  Tensor conv1(const Bott& b, const Tensor& xa) {
+    size_t w1 = pack_weights(b.c1, b.planes, b.inpl);
+    Affine a1 = conv_affine(b.c1, &b.bn2, b.planes);
+    Tensor t1 = talloc(xa.H, xa.W, b.planes);
+    conv(xa, w1, 1, b.inpl, b.planes, bn_for(b.planes), a1, true, nullptr, &t1, nullptr, nullptr, nullptr, fpp(b.c1));
+    return t1;
+  }
+
+  // Everything of bottleneck `b` behind its conv1, plus conv1 of the block that consumes its output:
+  //   y = conv3(relu(bn3(conv2(t1)))) + res (+ nearest_x2(up_add));   t1n = relu(next.bn2(next.conv1(relu(next.bn1(y)))))
+  // fuse == 2: one chain launch [3x3 -> conv3 -> next.conv1];  fuse == 1: 3x3 alone, then [conv3 -> next.conv1].
+  // t1 is consumed (freed).  `res` must have 2*planes channels (the caller applies a projection shortcut).
+  void tail(const Bott& b, const Tensor& res, Tensor& t1, const Bott* next, Tensor* y, Tensor* t1n,
+            const Tensor* up_add = nullptr) {
+    const int H = res.H, W = res.W, P = b.planes, O = 2 * b.planes;
+    StageSpec sp[3];
+    int n = 0;
+    size_t w2 = pack_weights(b.c2, P, P);
+    Affine a2 = conv_affine(b.c2, &b.bn3, P);
+    Tensor t2;
+    if (hg->fuse >= 2) {
+      StageSpec& s = sp[n++];
+      s.w_off = w2;
+      s.K = 9 * P;
+      s.N = P;
+      s.a1 = a2;
+      s.relu1 = true;
+      s.x_src = 1;
+      s.flop_per_px = fpp(b.c2);
+    } else {
+      t2 = talloc(H, W, P);
+      conv(t1, w2, 9, P, P, bn_for(P), a2, true, nullptr, &t2, nullptr, nullptr, nullptr, fpp(b.c2));
+      tfree(t1);
+    }
+    size_t w3 = pack_weights(b.c3, O, P);
+    Affine a3 = conv_affine(b.c3, nullptr, O);
+    *y = talloc(H, W, O);
+    Affine an{};
+    size_t w1n = 0;
+    Affine a1n{};
+    if (next) {
+      an = bn_affine(next->bn1, O);
+      w1n = pack_weights(next->c1, next->planes, next->inpl);
+      a1n = conv_affine(next->c1, &next->bn2, next->planes);
+      *t1n = talloc(H, W, next->planes);
+    }
+    if (hg->fuse < 2 && !next) {  // nothing to chain behind conv3: the stand-alone kernel does it
+      conv(t2, w3, 1, P, O, bn_for(O), a3, false, &res, y, nullptr, nullptr, nullptr, fpp(b.c3), up_add);
+      tfree(t2);
+      return;
+    }
+    {
+      StageSpec& s = sp[n++];
+      s.w_off = w3;
+      s.K = P;
+      s.N = O;
+      s.a1 = a3;
+      s.residual = &res;
+      s.res2_half = up_add;
+      s.out_raw = y;
+      s.x_src = next ? 2 : 0;
+      s.a2 = an;
+      s.flop_per_px = fpp(b.c3);
+    }
+    if (next) {
+      StageSpec& s = sp[n++];
+      s.w_off = w1n;
+      s.K = O;
+      s.N = next->planes;
+      s.a1 = a1n;
+      s.relu1 = true;
+      s.out_raw = t1n;
+      s.flop_per_px = fpp(next->c1);
+    }
+    if (hg->fuse >= 2) {
+      chain(t1, 9, P, sp, n);
+      tfree(t1);
+    } else {
+      chain(t2, 1, P, sp, n);
+      tfree(t2);
+    }
+  }
+
+  // fused form of hourglass(): x raw, t1_up = conv1 of hg[n-1][0] already applied to x.
+  void hourglass_f(const StackP& s, int n, const Tensor& x, Tensor& t1_up, const Bott* next, Tensor* o, Tensor* t1_o) {
+    Tensor p, pa;
+    pool(x, s.hg[n - 1][1].bn1, &p, &pa);
+    Tensor t1 = conv1(s.hg[n - 1][1], pa);
+    tfree(pa);
+    Tensor l1, t1n;
+    tail(s.hg[n - 1][1], p, t1, n > 1 ? &s.hg[n - 2][0] : &s.hg[0][3], &l1, &t1n);
+    tfree(p);
+    Tensor l2, t1l3;
+    if (n > 1)
+      hourglass_f(s, n - 1, l1, t1n, &s.hg[n - 1][2], &l2, &t1l3);
+    else
+      tail(s.hg[0][3], l1, t1n, &s.hg[0][2], &l2, &t1l3);
+    tfree(l1);
+    Tensor l3, none;
+    tail(s.hg[n - 1][2], l2, t1l3, nullptr, &l3, &none);
+    tfree(l2);
+    tail(s.hg[n - 1][0], x, t1_up, next, o, t1_o, &l3);
+    tfree(l3);
+  }
+
+  // stacks of the fused plan; x0 = output of layer3 (raw), t1 = conv1 of stack 0's hg[3][0] applied to it
+  void stacks_fused(Tensor x0, Tensor t1) {
+    const df3d_hg_desc& d = hg->desc;
+    const NetP& net = hg->net;
+    const int H4 = d.in_h / 4, W4 = d.in_w / 4;
+    const int S = d.num_stacks;
+    for (int i = 0; i < S; ++i) {
+      const StackP& s = net.stacks[i];
+      Tensor h, t1r;
+      hourglass_f(s, kDepth, x0, t1, &s.res, &h, &t1r);
+      const bool last = i == S - 1;
+      // [res.conv2 ->] res.conv3 + h -> fc + BN + ReLU [-> merged re-injection + x0 -> next stack's first conv1]
+      const Bott& b = s.res;
+      StageSpec sp[5];
+      int n = 0;
+      size_t w2 = pack_weights(b.c2, kFeats, kFeats);
+      Affine a2 = conv_affine(b.c2, &b.bn3, kFeats);
+      Tensor t2;
+      if (hg->fuse >= 2) {
+        StageSpec& q = sp[n++];
+        q.w_off = w2;
+        q.K = 9 * kFeats;
+        q.N = kFeats;
+        q.a1 = a2;
+        q.relu1 = true;
+        q.x_src = 1;
+        q.flop_per_px = fpp(b.c2);
+      } else {
+        t2 = talloc(H4, W4, kFeats);
+        conv(t1r, w2, 9, kFeats, kFeats, 128, a2, true, nullptr, &t2, nullptr, nullptr, nullptr, fpp(b.c2));
+        tfree(t1r);
+      }
+      {
+        StageSpec& q = sp[n++];  // r = conv3 + h (feeds fc raw: fc is conv -> BN -> ReLU)
+        q.w_off = pack_weights(b.c3, kCh, kFeats);
+        q.K = kFeats;
+        q.N = kCh;
+        q.a1 = conv_affine(b.c3, nullptr, kCh);
+        q.residual = &h;
+        q.x_src = 1;
+        q.flop_per_px = fpp(b.c3);
+      }
+      Tensor f, nx, t1x;
+      {
+        StageSpec& q = sp[n++];  // f = relu(bn(fc(r)))
+        q.w_off = pack_weights(s.fc, kCh, kCh);
+        q.K = kCh;
+        q.N = kCh;
+        q.a1 = conv_affine(s.fc, &s.fc_bn, kCh);
+        q.relu1 = true;
+        q.flop_per_px = fpp(s.fc);
+        if (last) {
+          f = talloc(H4, W4, kCh);
+          q.out_raw = &f;
+        } else {
+          q.x_src = 1;
+        }
+      }
+      if (!last) {
+        const Bott& nb0 = net.stacks[i + 1].hg[kDepth - 1][0];
+        Convp merged = merged_skip(s, i);
+        {
+          StageSpec& q = sp[n++];  // x' = x + fc_(f) + score_(score(f)) as one merged conv (see merged_skip)
+          q.w_off = pack_weights(merged, kCh, kCh);
+          q.K = kCh;
+          q.N = kCh;
+          q.a1 = conv_affine(merged, nullptr, kCh);
+          q.residual = &x0;
+          nx = talloc(H4, W4, kCh);
+          q.out_raw = &nx;
+          q.x_src = 2;
+          q.a2 = bn_affine(nb0.bn1, kCh);
+          q.flop_per_px = fpp(s.fc_) + fpp(s.score) + fpp(s.score_);
+        }
+        {
+          StageSpec& q = sp[n++];  // first conv1 of the next stack
+          q.w_off = pack_weights(nb0.c1, nb0.planes, nb0.inpl);
+          q.K = kCh;
+          q.N = nb0.planes;
+          q.a1 = conv_affine(nb0.c1, &nb0.bn2, nb0.planes);
+          q.relu1 = true;
+          t1x = talloc(H4, W4, nb0.planes);
+          q.out_raw = &t1x;
+          q.flop_per_px = fpp(nb0.c1);
+        }
+      }
+      if (hg->fuse >= 2) {
+        chain(t1r, 9, kFeats, sp, n);
+        tfree(t1r);
+      } else {
+        chain(t2, 1, kFeats, sp, n);
+        tfree(t2);
+      }
+      tfree(h);
+      tfree(x0);
+      if (last) {
+        size_t wsc = pack_weights(s.score, kHeatPad, kCh);
+        Affine as = conv_affine(s.score, nullptr, kHeatPad);
+        Tensor heat = talloc(H4, W4, kHeatPad, 4);
+        conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat, fpp(s.score));
+        tfree(f);
+        if (!dry && !err) {
+          Op op;
+          op.kind = OP_ARGMAX;
+          op.in0 = ptr(heat);
+          op.H = H4;
+          op.W = W4;
+          op.C = kHeatPad;
+          hg->ops.push_back(op);
+          hg->heat_ptr = ptr(heat);
+        }
+        tfree(heat);
+      } else {
+        x0 = nx;
+        t1 = t1x;
+      }
+    }
+  }
+
   void pool(const Tensor& x, const BNp& bn, Tensor* p, Tensor* pa) {
     Affine a = bn_affine(bn, x.C);
     *p = talloc(x.H / 2, x.W / 2, x.C);
@@ -544,6 +851,22 @@ struct Emitter {
     bottleneck(net.layer2, p, pa, &net.layer3.bn1, &y2, &y2a);
     tfree(p);
     tfree(pa);
+    if (hg->fuse > 0) {
+      // layer3 through the chain path: conv1 and the projection shortcut stand alone, the rest is a chain
+      // that ends in conv1 of the first hourglass bottleneck
+      Tensor t1 = conv1(net.layer3, y2a);
+      tfree(y2a);
+      size_t wd = pack_weights(net.layer3.ds, kCh, 2 * kInplanes);
+      Affine ad = conv_affine(net.layer3.ds, nullptr, kCh);
+      Tensor dres = talloc(H4, W4, kCh);
+      conv(y2, wd, 1, 2 * kInplanes, kCh, 256, ad, false, nullptr, &dres, nullptr, nullptr, nullptr, fpp(net.layer3.ds));
+      tfree(y2);
+      Tensor xf, t1x;
+      tail(net.layer3, dres, t1, &net.stacks[0].hg[kDepth - 1][0], &xf, &t1x);
+      tfree(dres);
+      stacks_fused(xf, t1x);
+      return;
+    }
     Tensor x0, x0a;
     bottleneck(net.layer3, y2, y2a, &net.stacks[0].hg[kDepth - 1][0].bn1, &x0, &x0a);
     tfree(y2);
@@ -645,6 +968,18 @@ static int lanes_for(const df3d_hg_desc& d) {
   return l;
 }
 
+static int fuse_for() {
+  // 2: 3x3-led conv chains; 1 (default, fastest measured so far): point-wise chains behind stand-alone
+  // 3x3 convs; 0: one launch per conv.  All three produce bit-identical results (tests/test_gpu_hourglass.py); the knob exists for
+  // that test and for profiling.
+  int f = 1;
+  if (const char* env = getenv("DF3D_HG_FUSE")) {
+    const int v = atoi(env);
+    if (v >= 0 && v <= 2) f = v;
+  }
+  return f;
+}
+
 static int chunk_for(const df3d_hg_desc& d, int lanes) {
   // images per lane and launch sequence.  Measured on B200 (profiles/): activations never fit the
   // 126 MB L2 at any useful chunk, and every launch costs ~10 us of fill/drain, so bigger is
@@ -666,6 +1001,7 @@ extern "C" size_t df3d_hg_workspace_bytes(const df3d_hg_desc* desc) {
   df3d_hg tmp;
   tmp.desc = *desc;
   tmp.n_lanes = lanes_for(*desc);
+  tmp.fuse = fuse_for();
   tmp.chunk = chunk_for(*desc, tmp.n_lanes);
   tmp.params.assign(param_count(*desc), 0.0f);
   Cursor c{tmp.params.data(), tmp.params.size()};
@@ -689,9 +1025,11 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
                prop.major, prop.minor);
   if (int e = tma_init()) return e;
   if (int e = conv_gemm_configure()) return e;
+  if (int e = conv_chain_configure()) return e;
 
   df3d_hg* hg = new df3d_hg();
   hg->desc = *desc;
+  hg->fuse = fuse_for();
   hg->num_sms = prop.multiProcessorCount;
   hg->n_lanes = lanes_for(*desc);
   hg->chunk = chunk_for(*desc, hg->n_lanes);
@@ -843,6 +1181,13 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
           if (int e = launch_conv_gemm(p, op.BN, sms, ls)) return e;
           break;
         }
+        case OP_CHAIN: {
+          ChainParams p = op.chain;
+          p.B = bc;
+          p.tiles_b = (bc + op.nb - 1) / op.nb;
+          if (int e = launch_conv_chain(p, sms, ls)) return e;
+          break;
+        }
         case OP_POOL:
           if (int e = launch_maxpool_bn_relu(reinterpret_cast<const __nv_bfloat16*>(op.in0), bc, op.H, op.W, op.C, op.scale,
                                              op.shift, reinterpret_cast<__nv_bfloat16*>(op.out0),
@@ -891,11 +1236,11 @@ extern "C" int df3d_hg_read_timing(df3d_hg* hg, double* out8) {
       DF3D_CUDA(cudaEventSynchronize(hg->events[(ci * n_ops + oi) * 2 + 1]));
       DF3D_CUDA(cudaEventElapsedTime(&ms, hg->events[(ci * n_ops + oi) * 2], hg->events[(ci * n_ops + oi) * 2 + 1]));
       const Op& op = hg->ops[oi];
-      if (op.kind == OP_CONV) {
+      if (op.kind == OP_CONV || op.kind == OP_CHAIN) {
         conv_ms += ms;
         conv_flops += op.flops_per_image * hg->timed_bc[ci];
         ++conv_n;
-        if (op.conv.taps == 9) {
+        if ((op.kind == OP_CONV ? op.conv.taps : op.chain.taps) == 9) {
           conv3_ms += ms;
           conv3_flops += op.flops_per_image * hg->timed_bc[ci];
           ++conv3_n;
@@ -947,6 +1292,19 @@ extern "C" int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, doub
     snprintf(desc, desc_len, "conv%dx%d %4dx%-4d cin=%3d BN=%3d%s%s%s", p.taps == 9 ? 3 : 1, p.taps == 9 ? 3 : 1, p.H, p.W,
              p.kc_per_tap * 64, op.BN, p.residual ? (p.has_res2 ? " +res+up" : " +res") : "", p.out_act ? " +act" : "",
              p.out_f32 ? " f32" : "");
+  } else if (op.kind == OP_CHAIN) {
+    const ChainParams& p = op.chain;
+    bpi = op.chain_bytes_per_image;
+    char shape[64];
+    int o = snprintf(shape, sizeof(shape), "%d", p.kc_per_tap * 64);
+    bool res = false, up = false;
+    for (int i = 0; i < p.n_chain; ++i) {
+      o += snprintf(shape + o, sizeof(shape) - o, ">%d", p.st[i].n);
+      res |= p.st[i].has_res != 0;
+      up |= p.st[i].has_res2 != 0;
+    }
+    snprintf(desc, desc_len, "chain%dx%d %4dx%-4d %s%s", p.taps == 9 ? 3 : 1, p.taps == 9 ? 3 : 1, p.H, p.W, shape,
+             up ? " +res+up" : (res ? " +res" : ""));
   } else if (op.kind == OP_POOL) {
     bpi = (double)op.H * op.W * op.C * 2.0 * 1.5;
     snprintf(desc, desc_len, "maxpool+bn  %4dx%-4d c=%3d", op.H, op.W, op.C);

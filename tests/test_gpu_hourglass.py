@@ -111,3 +111,27 @@ def test_batch_larger_than_chunk_is_consistent(hgmod, monkeypatch):
         ic, cc = eng_c.forward(img)
         torch.cuda.synchronize()
         assert torch.equal(ia, ic) and torch.equal(ca, cc)
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 128, 5), (2, 256, 512, 3), (8, 256, 256, 3), (2, 64, 64, 9)])
+def test_fused_plans_are_bit_identical(hgmod, monkeypatch, shape):
+    """The conv-chain plans (DF3D_HG_FUSE=1: point-wise chains behind stand-alone 3x3 convs, =2: 3x3-led
+    chains, the default) keep every rounding point of the one-launch-per-conv plan (=0): the bf16
+    intermediates that no longer go through HBM are rounded exactly as if they had been stored, so
+    score maps, arg-max indices and confidences must be bit-identical."""
+    stacks, H, W, B = shape
+    model = ohg.make_model(stacks, seed=7)
+    img = ohg.to_uint8(ohg.synthetic_images(B, H, W, seed=8)).cuda()
+    flip = torch.tensor([i % 2 for i in range(B)], dtype=torch.uint8).cuda()
+    outs = []
+    for fuse in ("0", "1", "2"):
+        monkeypatch.setenv("DF3D_HG_FUSE", fuse)
+        eng = hgmod.HourglassEngine(model.state_dict(), H, W, max_batch=B)
+        idx, conf, heat = eng.forward(img, flip=flip, return_heatmap=True)
+        torch.cuda.synchronize()
+        outs.append((idx.clone(), conf.clone(), heat[..., :19].clone(), eng.launches(B)))
+        eng.close()
+    for k in (1, 2):
+        assert torch.equal(outs[0][2], outs[k][2]), f"score maps differ between DF3D_HG_FUSE=0 and {k}"
+        assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][1], outs[k][1])
+    assert outs[2][3] < outs[1][3] < outs[0][3]        # fewer launches the more is chained
