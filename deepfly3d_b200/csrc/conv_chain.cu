@@ -36,6 +36,8 @@ constexpr int kMaxM = 8, kMaxW = 4, kMaxSlabs = 8;
 constexpr int kColP = 0, kColQ = 128, kColX = 384;
 constexpr int kChainSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int kChainBarBytes = 512;
+// specialised epilogues (see epi_slab)
+enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, kEpiResUpOut, kEpiResX };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -46,6 +48,90 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+
+// relu + round-to-nearest-even + pack in one instruction: {hi, lo} -> bf16x2 (lo in the low half)
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+// Epilogue of one 64-channel slab of one stage for one pixel row (one thread), fully specialised:
+//   UNIT  scale1 == 1 (conv without a folded BatchNorm): v = acc + shift1
+//   RES   + residual (bf16, swizzled slab row)     RES2  + nearest-x2 up-sampled half-resolution residual
+//   RELU  relu after the adds                      XSRC  0: no operand, 1: bf16(v), 2: relu(bn2(bf16(v)))
+//   OUT   bf16(v) to global memory
+// r: the 64 fp32 accumulator columns; c1/c2: this slab's first channel in the constant arrays.
+template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT>
+__device__ __forceinline__ void epi_slab(const uint32_t (&r)[2][32], const float4* __restrict__ sc1,
+                                         const float4* __restrict__ sh1, const float4* __restrict__ sc2,
+                                         const float4* __restrict__ sh2, const uint8_t* __restrict__ rrow,
+                                         const uint8_t* __restrict__ rrow2, uint32_t sw, uint32_t sw2, uint32_t x_addr,
+                                         uint8_t* out, bool store) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t xp[16], op[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 8 channels = one 16-byte chunk of the swizzled slab row
+      const int c4 = (half * 32 + j * 8) >> 2;
+      float v[8];
+      {
+        const float4 ha = sh1[c4], hb = sh1[c4 + 1];
+        const float t1[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        if (UNIT) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[half][j * 8 + e]) + t1[e];
+        } else {
+          const float4 sa = sc1[c4], sb = sc1[c4 + 1];
+          const float s1[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[half][j * 8 + e]), s1[e], t1[e]);
+        }
+      }
+      if (RES) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(half * 4 + j) ^ sw) << 4));
+        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[2 * e] += bf_lo(rw[e]);
+          v[2 * e + 1] += bf_hi(rw[e]);
+        }
+      }
+      if (RES2) {  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
+        const uint4 rr = *reinterpret_cast<const uint4*>(rrow2 + (((uint32_t)(half * 4 + j) ^ sw2) << 4));
+        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t pk = pack2(v[2 * e], v[2 * e + 1]);
+          v[2 * e] = bf_lo(pk) + bf_lo(rw[e]);
+          v[2 * e + 1] = bf_hi(pk) + bf_hi(rw[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) op[j * 4 + e] = RELU ? pack2_relu(v[2 * e], v[2 * e + 1]) : pack2(v[2 * e], v[2 * e + 1]);
+      if (XSRC == 2) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
+        const float4 sa = sc2[c4], sb = sc2[c4 + 1], ha = sh2[c4], hb = sh2[c4 + 1];
+        const float s2[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float t2[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t ow = op[j * 4 + e];
+          xp[j * 4 + e] = pack2_relu(fmaf(bf_lo(ow), s2[2 * e], t2[2 * e]), fmaf(bf_hi(ow), s2[2 * e + 1], t2[2 * e + 1]));
+        }
+      }
+    }
+    if (XSRC == 1) tmem_st_32x16(x_addr + half * 16, op);
+    if (XSRC == 2) tmem_st_32x16(x_addr + half * 16, xp);
+    if (OUT) {
+      if (store) {  // 32 channels = 64 contiguous bytes of this thread's pixel: two full 32-byte sectors
+        stg256(out + half * 64, op);
+        stg256(out + half * 64 + 32, op + 8);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __grid_constant__ ChainParams p) {
@@ -219,13 +305,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const uint32_t d0 = tmem_base + (uint32_t)p.st[0].acc_col;
       const uint32_t reg0 = p.st[0].acc_col == kColP ? 0u : 1u;
       uint32_t mu = 0, mph = 0, wu = 0, wph = 0, xuse = 0, use0 = 0, use1 = 0;
+      unsigned long long* const dbg = blockIdx.x == 0 ? p.dbg : nullptr;
+      int di = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         // ---- head: A and B from shared memory
         {
           uint32_t& use = reg0 ? use1 : use0;
+          if (dbg && di < 4000) dbg[di++] = clock64();  // [tile start]
           mbar_wait(rempty(reg0), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
           ++use;
           tc_fence_after();
+          if (dbg && di < 4000) dbg[di++] = clock64();  // [head accumulator free]
 #pragma unroll 1
           for (int kb = 0; kb < kb0; ++kb) {
             mbar_wait(mfull(mu), mph);
@@ -253,6 +343,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             umma_commit(mempty(ua));
           }
           umma_commit(rfull(reg0));
+          if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
         }
         // ---- later stages: A from tensor memory (X), B from the weight ring
 #pragma unroll 1
@@ -265,6 +356,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           mbar_wait(xfull, xuse & 1u);  // operand of this stage is complete in tensor memory
           ++xuse;
           tc_fence_after();
+          if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
 #pragma unroll 1
           for (int kb = 0; kb < kbn; ++kb) {
             const uint32_t xa = tmem_base + kColX + kb * 32;
@@ -284,6 +376,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             }
           }
           umma_commit(rfull(reg));  // accumulator ready; the operand in X may be overwritten
+          if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
         }
       }
     }
@@ -306,6 +399,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
     uint32_t use0 = 0, use1 = 0;
     uint32_t scount = 0;
+    unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
+    int di = 4096 * (1 + grp);
+    const int dend = di + 4000;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, n0;
       decode_tile(tile, x0, y0, n0);
@@ -314,8 +410,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       for (int i = 0; i < n_chain; ++i) {
         const ChainStage& st = p.st[i];
         const uint32_t reg = st.acc_col == kColP ? 0u : 1u;
-        const bool has_res = st.has_res != 0, has_res2 = st.has_res2 != 0;
-        const int x_src = st.x_src;
+        const bool has_res = st.has_res != 0;
+        const int x_src = st.x_src, kind = st.epi_kind;
         const int nsl = st.n >> 6;
         uint8_t* const out_row = st.out_raw ? reinterpret_cast<uint8_t*>(st.out_raw) + pixel * (size_t)st.n * 2 : nullptr;
         const float4* const sc1 = reinterpret_cast<const float4*>(sm + (aff_base - smem_base)) + (st.aff_off >> 2);
@@ -328,6 +424,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           ++use;
         }
         tc_fence_after();
+        if (dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
         const uint32_t t_row = tmem_base + lane_base + (uint32_t)st.acc_col;
         const uint32_t x_row = tmem_base + lane_base + kColX;
 #pragma unroll 1
@@ -344,67 +441,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           const uint8_t* const rrow = sm + (slab - smem_base) + row_off;
           const uint8_t* const rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off;
+          const float4 *c1 = sc1 + sl * 16, *h1 = sh1 + sl * 16, *c2 = sc2 + sl * 16, *h2 = sh2 + sl * 16;
+          const uint32_t xa = x_row + sl * 32;
+          uint8_t* const o = out_row + sl * 128;
           tmem_ld_wait();
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t xp[16], op[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 8 channels = one 16-byte chunk of the swizzled slab row
-              const int c4 = (sl * 64 + half * 32 + j * 8) >> 2;
-              const uint32_t chunk = ((uint32_t)(half * 4 + j) ^ sw) << 4;
-              float v[8];
-              {
-                const float4 sa = sc1[c4], sb = sc1[c4 + 1], ha = sh1[c4], hb = sh1[c4 + 1];
-                const float s1[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                const float t1[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[half][j * 8 + e]), s1[e], t1[e]);
-              }
-              if (has_res) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + chunk);
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[2 * e] += __uint_as_float(rw[e] << 16);
-                  v[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-                }
-              }
-              if (has_res2) {  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
-                const uint4 rr = *reinterpret_cast<const uint4*>(rrow2 + (((uint32_t)(half * 4 + j) ^ sw2) << 4));
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t pk = pack2(v[2 * e], v[2 * e + 1]);
-                  v[2 * e] = __uint_as_float(pk << 16) + __uint_as_float(rw[e] << 16);
-                  v[2 * e + 1] = __uint_as_float(pk & 0xffff0000u) + __uint_as_float(rw[e] & 0xffff0000u);
-                }
-              }
-              if (st.relu1) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) op[j * 4 + e] = pack2(v[2 * e], v[2 * e + 1]);
-              if (x_src == 2) {
-                const float4 sa = sc2[c4], sb = sc2[c4 + 1], ha = sh2[c4], hb = sh2[c4 + 1];
-                const float s2[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                const float t2[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
-                  const uint32_t ow = op[j * 4 + e];
-                  const float w0 = fmaxf(fmaf(__uint_as_float(ow << 16), s2[2 * e], t2[2 * e]), 0.0f);
-                  const float w1 = fmaxf(fmaf(__uint_as_float(ow & 0xffff0000u), s2[2 * e + 1], t2[2 * e + 1]), 0.0f);
-                  xp[j * 4 + e] = pack2(w0, w1);
-                }
-              }
-            }
-            if (x_src == 1) tmem_st_32x16(x_row + sl * 32 + half * 16, op);
-            if (x_src == 2) tmem_st_32x16(x_row + sl * 32 + half * 16, xp);
-            if (out_row && in_batch) {  // 32 channels = 64 contiguous bytes of this thread's pixel
-              uint8_t* const o = out_row + (sl * 64 + half * 32) * 2;
-              stg256(o, op);
-              stg256(o + 32, op + 8);
-            }
+          switch (kind) {  //         UNIT   RES    RES2   RELU  XSRC OUT
+            case kEpiReluX:    epi_slab<false, false, false, true, 1, false>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiReluOut:  epi_slab<false, false, false, true, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiResOut:   epi_slab<true, true, false, false, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiResUpOut: epi_slab<true, true, true, false, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            case kEpiResX:     epi_slab<true, true, false, false, 1, false>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
+            default: break;  // launch_conv_chain rejects anything else
           }
           if (has_res) {  // slab consumed by this warp
             __syncwarp();
@@ -419,6 +468,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           if (x_src) mbar_arrive(xfull);
           mbar_arrive(rempty(reg));
         }
+        if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
       }
     }
   }
@@ -450,6 +500,22 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
     DF3D_REQUIRE(!st.has_res2 || (st.has_res && p.tw % 2 == 0 && p.th % 2 == 0), DF3D_EUNSUPPORTED,
                  "launch_conv_chain: the half-resolution residual needs a full-resolution residual and an even tile");
     DF3D_REQUIRE(st.x_src || st.out_raw, DF3D_EINVAL, "launch_conv_chain: the last stage must store its output");
+    {
+      const bool relu = st.relu1 != 0, res = st.has_res != 0, up = st.has_res2 != 0, out = st.out_raw != nullptr;
+      const bool unit = st.unit_scale != 0;
+      int kind = -1;
+      if (!unit && !res && !up && relu && st.x_src == 1 && !out) kind = kEpiReluX;
+      if (!unit && !res && !up && relu && st.x_src == 0 && out) kind = kEpiReluOut;
+      if (unit && res && !up && !relu && st.x_src == 2 && out) kind = kEpiResOutAct;
+      if (unit && res && up && !relu && st.x_src == 2 && out) kind = kEpiResUpOutAct;
+      if (unit && res && !up && !relu && st.x_src == 0 && out) kind = kEpiResOut;
+      if (unit && res && up && !relu && st.x_src == 0 && out) kind = kEpiResUpOut;
+      if (unit && res && !up && !relu && st.x_src == 1 && !out) kind = kEpiResX;
+      DF3D_REQUIRE(kind >= 0, DF3D_EUNSUPPORTED,
+                   "launch_conv_chain: stage %d has no specialised epilogue (unit %d res %d up %d relu %d x %d out %d)", i,
+                   (int)unit, (int)res, (int)up, (int)relu, st.x_src, (int)out);
+      st.epi_kind = kind;
+    }
     st.aff_off = aff_floats;
     aff_floats += 4 * st.n;
     any_slab |= st.has_res != 0;

@@ -32,10 +32,12 @@ struct ChainStage {
   int n;         // output channels: 128 or 256
   int kblocks;   // K / 64 (head: taps * Cin/64; later stages: n of the previous stage / 64)
   int relu1;
+  int unit_scale;  // scale1 is identically 1 (conv without a folded BatchNorm): the epilogue only adds shift1
   int has_res, has_res2;
   int x_src;     // operand handed to the next stage: 0 none (last stage), 1 raw, 2 act
   int acc_col;   // TMEM column of this stage's accumulator (filled by launch_conv_chain)
   int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)
+  int epi_kind;  // specialised epilogue variant (filled by the launcher)
 };
 
 struct ChainParams {
@@ -53,6 +55,9 @@ struct ChainParams {
   int n_slabs;     // residual slabs (TMA prefetch ring)
   int slab_bytes;  // 16384 (+4096 with a half-resolution residual)
   int aff_bytes;
+  // profiling only (tools/chain_probe.cu): when non-null, CTA 0 records clock64() time stamps of its MMA
+  // issuer ([0, 4096)) and of epilogue warps 4 and 8 ([4096, 8192), [8192, 12288))
+  unsigned long long* dbg;
 };
 
 int conv_chain_configure();

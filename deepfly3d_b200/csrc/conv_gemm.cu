@@ -158,29 +158,38 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and operands: descriptors live in
+    // uniform registers, no per-lane waterfall around each tcgen05 instruction); one elected lane
+    // issues.  The issue rate of this loop bounds the tensor pipe.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      const uint64_t desc_hi = umma_smem_desc_sw128(0);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+#pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(a_addr(stage));
-          const uint64_t bdesc = umma_smem_desc_sw128(b_addr(stage));
+          const uint64_t adesc = desc_hi | (uint64_t)((a_addr(stage) >> 4) & 0x3FFFu);
+          const uint64_t bdesc = desc_hi | (uint64_t)((b_addr(stage) >> 4) & 0x3FFFu);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+            for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == (uint32_t)n_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
   } else if (warp == 2) {

@@ -469,6 +469,7 @@ struct Emitter {
     size_t w_off = 0;
     int K = 0, N = 0;  // packed weights [N][K]
     Affine a1{};
+    bool unit_scale = false;  // a1 comes from a conv without BatchNorm: scale == 1
     bool relu1 = false;
     const Tensor* residual = nullptr;
     const Tensor* res2_half = nullptr;
@@ -510,6 +511,7 @@ struct Emitter {
       st.n = s.N;
       st.kblocks = s.K / 64;
       st.relu1 = s.relu1 ? 1 : 0;
+      st.unit_scale = s.unit_scale ? 1 : 0;
       st.scale1 = hg->d_a + s.a1.scale_off;
       st.shift1 = hg->d_a + s.a1.shift_off;
       st.x_src = s.x_src;
@@ -600,6 +602,7 @@ struct Emitter {
       s.K = P;
       s.N = O;
       s.a1 = a3;
+      s.unit_scale = true;
       s.residual = &res;
       s.res2_half = up_add;
       s.out_raw = y;
@@ -686,6 +689,7 @@ struct Emitter {
         q.K = kFeats;
         q.N = kCh;
         q.a1 = conv_affine(b.c3, nullptr, kCh);
+        q.unit_scale = true;
         q.residual = &h;
         q.x_src = 1;
         q.flop_per_px = fpp(b.c3);
@@ -715,6 +719,7 @@ struct Emitter {
           q.K = kCh;
           q.N = kCh;
           q.a1 = conv_affine(merged, nullptr, kCh);
+          q.unit_scale = true;
           q.residual = &x0;
           nx = talloc(H4, W4, kCh);
           q.out_raw = &nx;
