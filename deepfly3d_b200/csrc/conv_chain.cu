@@ -1,26 +1,31 @@
 // tcgen05 convolution-chain kernel (see conv_chain.cuh).
 //
 // One persistent CTA per SM, 12 warps, 128-pixel tiles:
-//   warp 0  TMA producer of the head ring: A tiles (one 4-D box per tap and 64-channel block; the
-//           3x3 halo is the TMA's out-of-bounds zero fill) and the head's weight half-tiles
-//   warp 1  MMA issuer (one thread) + TMEM owner
+//   warp 0  TMA producer of the operand ring, in the MMA warp's issue order: per 64-wide K block of the head
+//           one A tile (a 4-D box per tap and channel block; the 3x3 halo is the TMA's out-of-bounds
+//           zero fill) + the head's weight half-tiles; per later stage 32 KB slots of weights
+//   warp 1  MMA issuer + TMEM owner (warp-uniform loop, one elected lane issues)
 //   warp 2  TMA producer of the residual slabs (64 channels x 128 pixels, + the half-resolution slab
 //           of the up-sample branch), a ring that prefetches across stages and tiles
-//   warp 3  TMA producer of the weight ring of stages >= 1 (prefetched while the head GEMM runs)
+//   warp 3  idle
 //   warps 4..11  epilogue: two groups of four warps (one TMEM lane quarter each), group g takes the
 //           64-channel slabs sl = g, g+2 of every stage
 //
-// Tensor memory (512 columns):  P = [0,128)  Q = [128,384)  accumulators,  X = [384,512) the bf16
-// operand of the next stage (128 lanes x up to 256 channels, two per column).  Stage i:
-//   MMA   : D(acc_i) = A_i * W_i^T, A_0 from shared memory (TMA), A_i (i >= 1) from X
-//   epilogue: tcgen05.ld acc_i -> scale/shift (+ residuals) -> ReLU / bf16 rounding
-//             -> optional bf16 store straight from registers (each thread owns one pixel row: 64
-//                contiguous bytes per 32 channels = two full-sector 256-bit stores)
-//             -> optional next-BatchNorm + ReLU -> tcgen05.st into X
-// The chain of one tile is sequential (stage i+1 needs the whole operand of stage i), but the head
-// GEMM of the next tile is issued right behind the last stage and overlaps its epilogue, and both
-// rings keep prefetching across tiles.
+// Stage i of a tile:
+//   MMA      D(acc_i) = A_i * W_i^T;  A_0 from shared memory (TMA), A_i (i >= 1) from tensor memory
+//   epilogue tcgen05.ld acc_i -> scale/shift (+ residuals) -> ReLU / bf16 rounding
+//            -> optional bf16 store straight from registers (each thread owns one pixel row: 64
+//               contiguous bytes per 32 channels = two full-sector 256-bit stores)
+//            -> optional next-BatchNorm + ReLU -> tcgen05.st of the bf16 operand of stage i+1 IN PLACE
+//               over the first half of the accumulator columns it was computed from
+// Tensor memory holds three regions, P = [0,128), Q = [128,384), R = [384,512); launch_conv_chain maps
+// every accumulator (two 128-column halves for 256 channels) onto them so that a region is only
+// rewritten after its last reader.  The chain of one tile is sequential, but the issue ORDER is
+// software-pipelined: the head GEMM of tile t+1 is issued right behind stage `head_after` of tile t
+// (the stage with the longest epilogue), so the tensor pipe works on the next 3x3 conv while the
+// epilogue warps apply residual / BatchNorm / stores of this one.
 #include <cstdlib>
+#include <initializer_list>
 
 #include "conv_chain.cuh"
 #include "sm100.cuh"
@@ -29,13 +34,13 @@ namespace df3d {
 
 using namespace sm100;
 
-constexpr int kChainThreads = 384;
+constexpr int kChainThreads = 384;  // warpgroup 0: producer / MMA / slab producer / idle; warpgroups 1, 2: epilogue
 constexpr int kEpiWarp0c = 4;
 constexpr int kUnitBytes = 16384;       // 128 rows x 64 bf16: one A tile or one 128-row weight half-tile
-constexpr int kMaxM = 8, kMaxW = 4, kMaxSlabs = 8;
-constexpr int kColP = 0, kColQ = 128, kColX = 384;
+constexpr int kMaxM = 8, kMaxSlabs = 8;  // ring slots, residual slabs
+constexpr int kColP = 0, kColQ = 128, kColR = 384;
 constexpr int kChainSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
-constexpr int kChainBarBytes = 512;
+constexpr int kChainBarBytes = 1024;  // barriers, TMEM slot, StageLite table
 // specialised epilogues (see epi_slab)
 enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, kEpiResUpOut, kEpiResX };
 
@@ -43,6 +48,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// Per-stage fields the MMA and epilogue warps read every tile, copied to shared memory once: indexed
+// loads from the kernel-parameter constant bank miss the small constant cache and cost ~1000 cycles
+// per stage when done in sequence.
+struct StageLite {
+  unsigned long long out;  // bf16 output base or 0
+  int n, kblocks, has_res, x_src, kind, col0, col1, aff_off, unit, hz, hzd, pad;
+};
+static_assert(sizeof(StageLite) == 56, "StageLite layout");
+constexpr int kLiteStride = 64;
+
 // 32 bytes (one full sector) to global memory
 __device__ __forceinline__ void stg256(void* ptr, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
@@ -64,15 +79,21 @@ __device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 
 //   RES   + residual (bf16, swizzled slab row)     RES2  + nearest-x2 up-sampled half-resolution residual
 //   RELU  relu after the adds                      XSRC  0: no operand, 1: bf16(v), 2: relu(bn2(bf16(v)))
 //   OUT   bf16(v) to global memory
-// r: the 64 fp32 accumulator columns; c1/c2: this slab's first channel in the constant arrays.
+// t_slab: TMEM address of the slab's 64 fp32 accumulator columns (the operand is written back in place
+// over the first 32); c1/c2: this slab's first channel in the constant arrays.  One 32-column half at a
+// time keeps the live registers low: with 227 KB of shared memory there is no L1 left, so a spilled
+// register is an L2 round trip.
 template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT>
-__device__ __forceinline__ void epi_slab(const uint32_t (&r)[2][32], const float4* __restrict__ sc1,
+__device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restrict__ sc1,
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
                                          const float4* __restrict__ sh2, const uint8_t* __restrict__ rrow,
                                          const uint8_t* __restrict__ rrow2, uint32_t sw, uint32_t sw2, uint32_t x_addr,
                                          uint8_t* out, bool store) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_slab + half * 32, r);
+    tmem_ld_wait();
     uint32_t xp[16], op[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // 8 channels = one 16-byte chunk of the swizzled slab row
@@ -83,12 +104,12 @@ __device__ __forceinline__ void epi_slab(const uint32_t (&r)[2][32], const float
         const float t1[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
         if (UNIT) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[half][j * 8 + e]) + t1[e];
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]) + t1[e];
         } else {
           const float4 sa = sc1[c4], sb = sc1[c4 + 1];
           const float s1[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[half][j * 8 + e]), s1[e], t1[e]);
+          for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[j * 8 + e]), s1[e], t1[e]);
         }
       }
       if (RES) {
@@ -139,25 +160,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const sm = smem_raw + (smem_base - smem_u32(smem_raw));  // same place as a __shared__ pointer: plain
                                                                     // loads/stores the compiler may schedule
+  const int nh0 = p.st[0].n >> 7;
+  // ONE ring of equal slots feeds the tensor pipe in issue order: a head K block (A tile + its weight
+  // half-tiles) or 32 KB of later-stage weights per slot
+  const uint32_t slot_bytes = (uint32_t)p.slot_bytes;
   const uint32_t m_base = smem_base;
-  const uint32_t w_base = m_base + (uint32_t)p.n_m * kUnitBytes;
-  const uint32_t s_base = w_base + (uint32_t)p.n_w * kUnitBytes;
+  const uint32_t s_base = m_base + (uint32_t)p.n_m * slot_bytes;
   const uint32_t aff_base = s_base + (uint32_t)p.n_slabs * (uint32_t)p.slab_bytes;
   const uint32_t bar_base = aff_base + (uint32_t)p.aff_bytes;
   auto mfull = [&](uint32_t s) { return bar_base + 8u * s; };
   auto mempty = [&](uint32_t s) { return bar_base + 8u * (kMaxM + s); };
-  auto wfull = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + s); };
-  auto wempty = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + kMaxW + s); };
-  auto sfull = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxW + s); };
-  auto sempty = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxW + kMaxSlabs + s); };
-  auto rfull = [&](uint32_t r) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxW + 2 * kMaxSlabs + r); };
-  auto rempty = [&](uint32_t r) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxW + 2 * kMaxSlabs + 2 + r); };
-  const uint32_t xfull = bar_base + 8u * (2 * kMaxM + 2 * kMaxW + 2 * kMaxSlabs + 4);
-  const uint32_t tmem_slot = xfull + 8u;
+  auto sfull = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + s); };
+  auto sempty = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + kMaxSlabs + s); };
+  auto accfull = [&](uint32_t i) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + i); };
+  auto epidone = [&](uint32_t i) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + kMaxChain + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
+  const StageLite* const lite0 = reinterpret_cast<const StageLite*>(sm + (bar_base - smem_base) + 8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 64);
+  auto lite = [&](int i) -> const StageLite& { return *reinterpret_cast<const StageLite*>(reinterpret_cast<const uint8_t*>(lite0) + i * kLiteStride); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int n_chain = p.n_chain;
+  const int head_after = p.head_after;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA);
@@ -170,32 +194,48 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_init(mfull(s), 1);
       mbar_init(mempty(s), 1);
     }
-    for (int s = 0; s < p.n_w; ++s) {
-      mbar_init(wfull(s), 1);
-      mbar_init(wempty(s), 1);
-    }
     for (int s = 0; s < p.n_slabs; ++s) {
       mbar_init(sfull(s), 1);
       mbar_init(sempty(s), 4);  // one arrive per warp of the epilogue group that read it
     }
-    for (int r = 0; r < 2; ++r) {
-      mbar_init(rfull(r), 1);
-      mbar_init(rempty(r), 8);  // one arrive per epilogue warp
+    for (int i = 0; i < n_chain; ++i) {
+      mbar_init(accfull(i), 1);
+      mbar_init(epidone(i), 8);  // one arrive per epilogue warp
     }
-    mbar_init(xfull, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // per-channel epilogue constants of every stage -> shared memory: [scale1 n][shift1 n][scale2 n][shift2 n]
+  if (warp == 2 && lane < n_chain) {
+    const ChainStage& st = p.st[lane];
+    StageLite* l = const_cast<StageLite*>(&lite(lane));
+    l->out = reinterpret_cast<unsigned long long>(st.out_raw);
+    l->n = st.n;
+    l->kblocks = st.kblocks;
+    l->has_res = st.has_res;
+    l->x_src = st.x_src;
+    l->kind = st.epi_kind;
+    l->col0 = st.col[0];
+    l->col1 = st.col[1];
+    l->aff_off = st.aff_off;
+    l->unit = st.unit_scale;
+    l->hz = st.hz_stage;
+    l->hzd = st.hz_delta;
+  }
+  // per-channel epilogue constants of every stage -> shared memory, only the arrays the stage uses:
+  // [scale1 n (unless it is 1)][shift1 n][scale2 n][shift2 n (when the operand is relu(bn2(.)))]
   for (int i = 0; i < n_chain; ++i) {
     const ChainStage& st = p.st[i];
-    const uint32_t a0 = aff_base + 4u * (uint32_t)st.aff_off;
-    for (int c = threadIdx.x; c < st.n; c += kChainThreads) {
-      const float s2 = st.x_src == 2 ? st.scale2[c] : 0.f, h2 = st.x_src == 2 ? st.shift2[c] : 0.f;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * c), "f"(st.scale1[c]));
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (st.n + c)), "f"(st.shift1[c]));
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (2 * st.n + c)), "f"(s2));
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (3 * st.n + c)), "f"(h2));
+    uint32_t a0 = aff_base + 4u * (uint32_t)st.aff_off;
+    if (!st.unit_scale) {
+      for (int c = threadIdx.x; c < st.n; c += kChainThreads) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * c), "f"(st.scale1[c]));
+      a0 += 4u * st.n;
+    }
+    for (int c = threadIdx.x; c < st.n; c += kChainThreads) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * c), "f"(st.shift1[c]));
+    if (st.x_src == 2) {
+      for (int c = threadIdx.x; c < st.n; c += kChainThreads) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (st.n + c)), "f"(st.scale2[c]));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (2 * st.n + c)), "f"(st.shift2[c]));
+      }
     }
   }
   tc_fence_before();
@@ -205,71 +245,93 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   auto decode_tile = [&](int tile, int& x0, int& y0, int& n0) {
-    const int tx = tile % p.tiles_x;
-    tile /= p.tiles_x;
-    const int ty = tile % p.tiles_y;
-    const int tb = tile / p.tiles_y;
+    int tx, ty, tb;
+    if (p.tx_shift >= 0 && p.ty_shift >= 0) {
+      tx = tile & (p.tiles_x - 1);
+      ty = (tile >> p.tx_shift) & (p.tiles_y - 1);
+      tb = tile >> (p.tx_shift + p.ty_shift);
+    } else {
+      tx = tile % p.tiles_x;
+      tile /= p.tiles_x;
+      ty = tile % p.tiles_y;
+      tb = tile / p.tiles_y;
+    }
     x0 = tx * p.tw;
     y0 = ty * p.th;
     n0 = tb * p.nb;
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ head ring producer
+    // ------------------------------------------------------------------ ring producer (issue order of the MMA warp)
     if (lane == 0) {
-      const int kb0 = p.st[0].kblocks, nh0 = p.st[0].n >> 7;
+      const int kb0 = p.st[0].kblocks;
       uint32_t u = 0, ph = 0;
+      auto acquire = [&](uint32_t bytes) -> uint32_t {
+        mbar_wait(mempty(u), ph ^ 1u);
+        mbar_arrive_expect_tx(mfull(u), bytes);
+        return m_base + u * slot_bytes;
+      };
       auto advance = [&]() {
         if (++u == (uint32_t)p.n_m) {
           u = 0;
           ph ^= 1u;
         }
       };
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load_head = [&](int tile) {
         int x0, y0, n0;
         decode_tile(tile, x0, y0, n0);
+        int tap = 0, kc = 0;
         for (int kb = 0; kb < kb0; ++kb) {
-          const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
           int dx = 0, dy = 0;
           if (p.taps == 9) {
             dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+            dx = tap - (tap / 3) * 3 - 1;
           }
-          mbar_wait(mempty(u), ph ^ 1u);
-          mbar_arrive_expect_tx(mfull(u), kUnitBytes);
-          tma_load_4d(m_base + u * kUnitBytes, &p.tmA, mfull(u), kc * 64, x0 + dx, y0 + dy, n0);
+          const uint32_t dst = acquire((uint32_t)(1 + nh0) * kUnitBytes);
+          tma_load_4d(dst, &p.tmA, mfull(u), kc * 64, x0 + dx, y0 + dy, n0);
+          for (int h = 0; h < nh0; ++h) tma_load_2d(dst + (1 + h) * kUnitBytes, &p.st[0].tmB, mfull(u), kb * 64, h * 128);
           advance();
-          for (int h = 0; h < nh0; ++h) {
-            mbar_wait(mempty(u), ph ^ 1u);
-            mbar_arrive_expect_tx(mfull(u), kUnitBytes);
-            tma_load_2d(m_base + u * kUnitBytes, &p.st[0].tmB, mfull(u), kb * 64, h * 128);
-            advance();
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
           }
         }
-      }
-    }
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ weight ring producer (stages >= 1)
-    if (lane == 0 && n_chain > 1) {
-      uint32_t u = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int i = 1; i < n_chain; ++i) {
-          const int kbn = p.st[i].kblocks, nh = p.st[i].n >> 7;
-          for (int kb = 0; kb < kbn; ++kb)
-            for (int h = 0; h < nh; ++h) {
-              mbar_wait(wempty(u), ph ^ 1u);
-              mbar_arrive_expect_tx(wfull(u), kUnitBytes);
-              tma_load_2d(w_base + u * kUnitBytes, &p.st[i].tmB, wfull(u), kb * 64, h * 128);
-              if (++u == (uint32_t)p.n_w) {
-                u = 0;
-                ph ^= 1u;
-              }
-            }
+      };
+      // one 32 KB slot = both 128-row halves of one K block (256 outputs) or two K blocks (128 outputs)
+      auto load_weights = [&](int i) {
+        const int kbn = lite(i).kblocks, nh = lite(i).n >> 7;
+        const int slots = (kbn * nh) >> 1;
+        for (int sl = 0; sl < slots; ++sl) {
+          const uint32_t dst = acquire(2 * kUnitBytes);
+          if (nh == 2) {
+            tma_load_2d(dst, &p.st[i].tmB, mfull(u), sl * 64, 0);
+            tma_load_2d(dst + kUnitBytes, &p.st[i].tmB, mfull(u), sl * 64, 128);
+          } else {
+            tma_load_2d(dst, &p.st[i].tmB, mfull(u), (2 * sl) * 64, 0);
+            tma_load_2d(dst + kUnitBytes, &p.st[i].tmB, mfull(u), (2 * sl + 1) * 64, 0);
+          }
+          advance();
         }
+      };
+      // issue order (same walk in the MMA warp and in the epilogue warps): a virtual tile -1 runs only the
+      // head of tile 0; step s of tile t is stage s+1 (s < head_after), the head of tile t+1
+      // (s == head_after) or stage s (s > head_after)
+      const int stride = (int)gridDim.x;
+      for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
+        const bool has_next = tile + stride < total_tiles;
+        for (int sidx = 0; sidx < n_chain; ++sidx) {
+          const bool head_step = (n_chain == 1) || (sidx == head_after);
+          if (head_step) {
+            if (has_next) load_head(tile + stride);
+          } else if (t >= 0) {
+            load_weights(sidx < head_after ? sidx + 1 : sidx);
+          }
+        }
+        if (!has_next) break;
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ residual / staging slab producer
+    // ------------------------------------------------------------------ residual slab producer
     if (lane == 0 && p.n_slabs > 0) {
       uint32_t u = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -295,90 +357,117 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // One thread; the loop bodies are kept minimal (no local arrays, no unrolling across blocks):
-    // the issue rate of this thread bounds the tensor pipe.
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
-      const uint64_t desc_hi = umma_smem_desc_sw128(0);  // everything but the 14-bit start address
-      const uint32_t n_m = (uint32_t)p.n_m, n_w = (uint32_t)p.n_w;
-      const int kb0 = p.st[0].kblocks, nh0 = p.st[0].n >> 7;
-      const uint32_t d0 = tmem_base + (uint32_t)p.st[0].acc_col;
-      const uint32_t reg0 = p.st[0].acc_col == kColP ? 0u : 1u;
-      uint32_t mu = 0, mph = 0, wu = 0, wph = 0, xuse = 0, use0 = 0, use1 = 0;
-      unsigned long long* const dbg = blockIdx.x == 0 ? p.dbg : nullptr;
-      int di = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        // ---- head: A and B from shared memory
-        {
-          uint32_t& use = reg0 ? use1 : use0;
-          if (dbg && di < 4000) dbg[di++] = clock64();  // [tile start]
-          mbar_wait(rempty(reg0), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
-          ++use;
-          tc_fence_after();
-          if (dbg && di < 4000) dbg[di++] = clock64();  // [head accumulator free]
+    // The whole warp runs the loops (warp-uniform control flow and operands: descriptors live in
+    // uniform registers, no per-lane waterfall around each tcgen05 instruction); one elected lane issues.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint64_t desc_hi = umma_smem_desc_sw128(0);  // everything but the 14-bit start address
+    const uint32_t n_m = (uint32_t)p.n_m;
+    const int kb0 = p.st[0].kblocks;
+    const uint32_t d0 = tmem_base + (uint32_t)p.st[0].col[0], d1 = tmem_base + (uint32_t)p.st[0].col[1];
+    const int hz0 = p.st[0].hz_stage, hz0_delta = p.st[0].hz_delta;
+    uint32_t mu = 0, mph = 0;
+    unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+    int di = 0;
+
+    // head GEMM of local tile number `t` (A and B from shared memory)
+    auto issue_head = [&](int t) {
+      if (dbg && di < 4000) dbg[di++] = clock64();  // [head start]
+      if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait_warp(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
+      tc_fence_after();
 #pragma unroll 1
-          for (int kb = 0; kb < kb0; ++kb) {
-            mbar_wait(mfull(mu), mph);
-            const uint32_t ua = mu;
-            const uint64_t adesc = desc_hi | (uint64_t)(((m_base + mu * kUnitBytes) >> 4) & 0x3FFFu);
-            if (++mu == n_m) {
-              mu = 0;
-              mph ^= 1u;
-            }
-#pragma unroll 1
-            for (int h = 0; h < nh0; ++h) {
-              mbar_wait(mfull(mu), mph);
-              tc_fence_after();
-              const uint64_t bdesc = desc_hi | (uint64_t)(((m_base + mu * kUnitBytes) >> 4) & 0x3FFFu);
-              const uint32_t d = d0 + h * 128;
+      for (int kb = 0; kb < kb0; ++kb) {
+        mbar_wait_warp(mfull(mu), mph);
+        tc_fence_after();
+        const uint32_t a_addr = m_base + mu * slot_bytes;
+        const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+        const uint64_t b0 = desc_hi | (uint64_t)(((a_addr + kUnitBytes) >> 4) & 0x3FFFu);
+        const uint64_t b1 = desc_hi | (uint64_t)(((a_addr + 2 * kUnitBytes) >> 4) & 0x3FFFu);
+        if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
-                umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_commit(mempty(mu));  // frees the weight half-tile once these MMAs retire
-              if (++mu == n_m) {
-                mu = 0;
-                mph ^= 1u;
-              }
-            }
-            umma_commit(mempty(ua));
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
+            umma_bf16(d0, adesc + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (nh0 == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d1, adesc + 2u * k, b1 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(rfull(reg0));
-          if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
+          umma_commit(mempty(mu));  // frees the ring stage once these MMAs retire
         }
-        // ---- later stages: A from tensor memory (X), B from the weight ring
-#pragma unroll 1
-        for (int i = 1; i < n_chain; ++i) {
-          const int kbn = p.st[i].kblocks, nh = p.st[i].n >> 7, col = p.st[i].acc_col;
-          const uint32_t reg = col == kColP ? 0u : 1u;
-          uint32_t& use = reg ? use1 : use0;
-          mbar_wait(rempty(reg), (use & 1u) ^ 1u);
-          ++use;
-          mbar_wait(xfull, xuse & 1u);  // operand of this stage is complete in tensor memory
-          ++xuse;
-          tc_fence_after();
-          if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
-#pragma unroll 1
-          for (int kb = 0; kb < kbn; ++kb) {
-            const uint32_t xa = tmem_base + kColX + kb * 32;
-#pragma unroll 1
-            for (int h = 0; h < nh; ++h) {
-              mbar_wait(wfull(wu), wph);
-              tc_fence_after();
-              const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wu * kUnitBytes) >> 4) & 0x3FFFu);
-              const uint32_t d = tmem_base + (uint32_t)col + h * 128;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, xa + k * 8, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_commit(wempty(wu));
-              if (++wu == n_w) {
-                wu = 0;
-                wph ^= 1u;
-              }
-            }
-          }
-          umma_commit(rfull(reg));  // accumulator ready; the operand in X may be overwritten
-          if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
+        __syncwarp();
+        if (++mu == n_m) {
+          mu = 0;
+          mph ^= 1u;
         }
       }
+      if (elect_one()) umma_commit(accfull(0));
+      __syncwarp();
+      if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
+    };
+
+    // later stage i of local tile t: A from tensor memory (written in place by the previous epilogue), B from the ring
+    auto issue_stage = [&](int i, int t) {
+      const uint32_t par = (uint32_t)t & 1u;
+      const StageLite& L = lite(i);
+      const StageLite& Lp = lite(i - 1);
+      const int kbn = L.kblocks, nh = L.n >> 7;
+      const uint32_t c0 = tmem_base + (uint32_t)L.col0, c1 = tmem_base + (uint32_t)L.col1;
+      const uint32_t x0c = tmem_base + (uint32_t)Lp.col0, x1c = tmem_base + (uint32_t)Lp.col1;
+      const int hz = L.hz, hzd = L.hzd;
+      mbar_wait_warp(epidone(i - 1), par);  // operand of this stage is complete in tensor memory
+      if (hz >= 0 && t - hzd >= 0) mbar_wait_warp(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
+      tc_fence_after();
+      if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
+      const int slots = (kbn * nh) >> 1;
+#pragma unroll 1
+      for (int sl = 0; sl < slots; ++sl) {
+        mbar_wait_warp(mfull(mu), mph);
+        tc_fence_after();
+        const uint32_t b_addr = m_base + mu * slot_bytes;
+        const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+        const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kUnitBytes) >> 4) & 0x3FFFu);
+        if (elect_one()) {
+          if (nh == 2) {  // K block sl, both output halves
+            const uint32_t xa = ((sl >> 1) ? x1c : x0c) + (sl & 1) * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(c1, xa + k * 8, b1 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+          } else {        // K blocks 2 sl and 2 sl + 1 of a 128-wide stage
+            const uint32_t xa = sl ? x1c : x0c;  // K blocks 0,1 live in the first operand half, 2,3 in the second
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + 64 + k * 8, b1 + 2u * k, idesc, 1u);
+          }
+          umma_commit(mempty(mu));
+        }
+        __syncwarp();
+        if (++mu == n_m) {
+          mu = 0;
+          mph ^= 1u;
+        }
+      }
+      if (elect_one()) umma_commit(accfull(i));  // accumulator ready; the consumed operand may be overwritten
+      __syncwarp();
+      if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
+      if (p.dbg_exec) {  // probe only: how long until the accumulator is complete (serialises this warp)
+        mbar_wait_warp(accfull(i), par);
+        if (dbg && di < 4000) dbg[di++] = clock64();
+      }
+    };
+
+    const int stride = (int)gridDim.x;
+    for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
+      const bool has_next = tile + stride < total_tiles;
+#pragma unroll 1
+      for (int sidx = 0; sidx < n_chain; ++sidx) {
+        const bool head_step = (n_chain == 1) || (sidx == head_after);
+        if (head_step) {
+          if (has_next) issue_head(t + 1);
+        } else if (t >= 0) {
+          issue_stage(sidx < head_after ? sidx + 1 : sidx, t);
+        }
+      }
+      if (!has_next) break;
     }
   } else if (warp >= kEpiWarp0c) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)
@@ -397,79 +486,95 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       row2_off = (uint32_t)r2 * 128u;
       sw2 = (uint32_t)(r2 & 7);
     }
-    uint32_t use0 = 0, use1 = 0;
-    uint32_t scount = 0;
+    uint32_t spos = 0, sphase = 0;  // ring position / phase of the next residual slab (slab 0 of the next stage with one)
+    const uint32_t n_slabs = (uint32_t)p.n_slabs;
     unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
     int di = 4096 * (1 + grp);
     const int dend = di + 4000;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int x0, y0, n0;
-      decode_tile(tile, x0, y0, n0);
+
+    // epilogue of stage i of the tile (local number t) at pixel offsets x0, y0, n0
+    auto run_stage = [&](int i, int t, int x0, int y0, int n0) {
+      const StageLite& st = lite(i);
       const bool in_batch = (n0 + pn) < p.B;  // partially filled multi-image tiles: skip the stores
       const size_t pixel = ((size_t)(n0 + pn) * p.H + (y0 + phh)) * p.W + (x0 + pw);
-      for (int i = 0; i < n_chain; ++i) {
-        const ChainStage& st = p.st[i];
-        const uint32_t reg = st.acc_col == kColP ? 0u : 1u;
-        const bool has_res = st.has_res != 0;
-        const int x_src = st.x_src, kind = st.epi_kind;
-        const int nsl = st.n >> 6;
-        uint8_t* const out_row = st.out_raw ? reinterpret_cast<uint8_t*>(st.out_raw) + pixel * (size_t)st.n * 2 : nullptr;
-        const float4* const sc1 = reinterpret_cast<const float4*>(sm + (aff_base - smem_base)) + (st.aff_off >> 2);
-        const float4* const sh1 = sc1 + (st.n >> 2);
-        const float4* const sc2 = sh1 + (st.n >> 2);
-        const float4* const sh2 = sc2 + (st.n >> 2);
-        {
-          uint32_t& use = reg ? use1 : use0;
-          mbar_wait(rfull(reg), use & 1u);
-          ++use;
-        }
-        tc_fence_after();
-        if (dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
-        const uint32_t t_row = tmem_base + lane_base + (uint32_t)st.acc_col;
-        const uint32_t x_row = tmem_base + lane_base + kColX;
+      const bool has_res = st.has_res != 0;
+      const int x_src = st.x_src, kind = st.kind;
+      const int nsl = st.n >> 6;
+      uint8_t* const out_row = st.out ? reinterpret_cast<uint8_t*>(st.out) + pixel * (size_t)st.n * 2 : nullptr;
+      const float4* const sc1 = reinterpret_cast<const float4*>(sm + (aff_base - smem_base)) + (st.aff_off >> 2);
+      const float4* const sh1 = sc1 + (st.unit ? 0 : (st.n >> 2));
+      const float4* const sc2 = sh1 + (st.n >> 2);
+      const float4* const sh2 = sc2 + (st.n >> 2);
+      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i entered]
+      mbar_wait_warp(accfull(i), (uint32_t)t & 1u);
+      tc_fence_after();
+      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
+      const uint32_t t_lo = tmem_base + lane_base + (uint32_t)st.col0, t_hi = tmem_base + lane_base + (uint32_t)st.col1;
 #pragma unroll 1
-        for (int sl = grp; sl < nsl; sl += 2) {
-          uint32_t su = 0, slab = s_base;
-          uint32_t r[2][32];
-          tmem_ld_32x32(t_row + sl * 64, r[0]);  // both halves in flight while the residual slab is awaited
-          tmem_ld_32x32(t_row + sl * 64 + 32, r[1]);
-          if (has_res) {
-            const uint32_t idx = scount + (uint32_t)sl;
-            su = idx % (uint32_t)p.n_slabs;
-            mbar_wait(sfull(su), (idx / (uint32_t)p.n_slabs) & 1u);
-            slab = s_base + su * (uint32_t)p.slab_bytes;
+      for (int sl = grp; sl < nsl; sl += 2) {
+        uint32_t su = 0, slab = s_base;
+        const uint32_t t_slab = ((sl >> 1) ? t_hi : t_lo) + (sl & 1) * 64;
+        if (has_res) {
+          su = spos + (uint32_t)sl;
+          uint32_t sph = sphase;
+          while (su >= n_slabs) {
+            su -= n_slabs;
+            sph ^= 1u;
           }
-          const uint8_t* const rrow = sm + (slab - smem_base) + row_off;
-          const uint8_t* const rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off;
-          const float4 *c1 = sc1 + sl * 16, *h1 = sh1 + sl * 16, *c2 = sc2 + sl * 16, *h2 = sh2 + sl * 16;
-          const uint32_t xa = x_row + sl * 32;
-          uint8_t* const o = out_row + sl * 128;
-          tmem_ld_wait();
-          switch (kind) {  //         UNIT   RES    RES2   RELU  XSRC OUT
-            case kEpiReluX:    epi_slab<false, false, false, true, 1, false>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiReluOut:  epi_slab<false, false, false, true, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiResOut:   epi_slab<true, true, false, false, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiResUpOut: epi_slab<true, true, true, false, 0, true>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            case kEpiResX:     epi_slab<true, true, false, false, 1, false>(r, c1, h1, c2, h2, rrow, rrow2, sw, sw2, xa, o, in_batch); break;
-            default: break;  // launch_conv_chain rejects anything else
-          }
-          if (has_res) {  // slab consumed by this warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sempty(su));
-          }
+          mbar_wait_warp(sfull(su), sph);
+          slab = s_base + su * (uint32_t)p.slab_bytes;
         }
-        if (has_res) scount += (uint32_t)nsl;
-        if (x_src) tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (x_src) mbar_arrive(xfull);
-          mbar_arrive(rempty(reg));
+        const uint8_t* const rrow = sm + (slab - smem_base) + row_off;
+        const uint8_t* const rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off;
+        const float4 *c1 = sc1 + sl * 16, *h1 = sh1 + sl * 16, *c2 = sc2 + sl * 16, *h2 = sh2 + sl * 16;
+        uint8_t* const o = out_row + sl * 128;
+        // the operand of the next stage replaces the first 32 of the 64 columns just read (in place)
+        switch (kind) {  //          UNIT   RES    RES2   RELU  XSRC OUT
+          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          default: break;  // launch_conv_chain rejects anything else
         }
-        if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
+        if (has_res) {  // slab consumed by this warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sempty(su));
+        }
       }
+      if (has_res) {
+        spos += (uint32_t)nsl;
+        while (spos >= n_slabs) {
+          spos -= n_slabs;
+          sphase ^= 1u;
+        }
+      }
+      if (x_src) tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epidone(i));
+      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
+    };
+
+    const int stride = (int)gridDim.x;
+    int x0 = 0, y0 = 0, n0 = 0;
+    for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
+      const bool has_next = tile + stride < total_tiles;
+      int nx0 = 0, ny0 = 0, nn0 = 0;
+      if (has_next) decode_tile(tile + stride, nx0, ny0, nn0);
+#pragma unroll 1
+      for (int sidx = 0; sidx < n_chain; ++sidx) {
+        const bool head_step = (n_chain == 1) || (sidx == head_after);
+        if (head_step ? !has_next : (t < 0)) continue;
+        const int i = head_step ? 0 : (sidx < head_after ? sidx + 1 : sidx);
+        run_stage(i, head_step ? t + 1 : t, head_step ? nx0 : x0, head_step ? ny0 : y0, head_step ? nn0 : n0);
+      }
+      if (!has_next) break;
+      x0 = nx0;
+      y0 = ny0;
+      n0 = nn0;
     }
   }
 
@@ -481,6 +586,77 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 // ------------------------------------------------------------------------------------------ host
 int conv_chain_configure() {
   DF3D_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemLimit));
+  return DF3D_OK;
+}
+
+// Tensor-memory plan of a chain: accumulator columns per stage, where in the issue order the next
+// tile's head GEMM goes, and the one epilogue each stage has to wait for before it may overwrite its
+// accumulator columns (the operand dependency on the previous stage is implicit).  Rules:
+//   * the operand of stage i+1 lives in place in the accumulator columns of stage i, so those columns
+//     stay busy until stage i+1 has been issued (the tensor pipe executes in issue order);
+//   * a hazard (stage j, delta) means "epilogue j of tile t - delta"; with delta = 1, j >= i keeps the
+//     parity wait unambiguous (epilogue j of tile t cannot have completed yet).
+static int plan_tmem(ChainParams& p) {
+  const int n = p.n_chain;
+  auto set = [&](int i, int lo, int hi, int hz, int delta) {
+    p.st[i].col[0] = lo;
+    p.st[i].col[1] = hi;
+    p.st[i].hz_stage = hz;
+    p.st[i].hz_delta = delta;
+  };
+  int w[kMaxChain] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < n; ++i) w[i] = p.st[i].n;
+  auto is = [&](std::initializer_list<int> pat) {
+    if ((int)pat.size() != n) return false;
+    int i = 0;
+    for (int v : pat)
+      if (w[i++] != v) return false;
+    return true;
+  };
+  if (is({128, 256, 128})) {  // bottleneck tail + next conv1: P | Q | R, next head behind conv3
+    set(0, kColP, kColP, -1, 0);
+    set(1, kColQ, kColQ + 128, -1, 0);
+    set(2, kColR, kColR, 2, 1);
+    p.head_after = 1;
+  } else if (is({128, 256})) {  // bottleneck tail alone
+    set(0, kColP, kColP, -1, 0);
+    set(1, kColQ, kColQ + 128, 1, 1);
+    p.head_after = 1;
+  } else if (is({128, 256, 256, 256, 128})) {  // inter-stack chain: P | Q | P+R | Q | R, next head behind the merged conv
+    set(0, kColP, kColP, -1, 0);
+    set(1, kColQ, kColQ + 128, -1, 0);
+    set(2, kColP, kColR, 4, 1);
+    set(3, kColQ, kColQ + 128, -1, 0);
+    set(4, kColR, kColR, -1, 0);
+    p.head_after = 3;
+  } else if (is({128, 256, 256})) {  // last stack: P | Q | P+R; the next head has to wait for the fc epilogue
+    set(0, kColP, kColP, 2, 1);
+    set(1, kColQ, kColQ + 128, -1, 0);
+    set(2, kColP, kColR, -1, 0);
+    p.head_after = 2;
+  } else if (is({256, 128})) {  // point-wise chains behind a stand-alone 3x3 conv
+    set(0, kColQ, kColQ + 128, -1, 0);
+    set(1, kColP, kColP, 1, 1);
+    p.head_after = 1;
+  } else if (is({256, 256, 256, 128})) {
+    set(0, kColQ, kColQ + 128, -1, 0);
+    set(1, kColP, kColR, 3, 1);
+    set(2, kColQ, kColQ + 128, -1, 0);
+    set(3, kColP, kColP, -1, 0);
+    p.head_after = 3;
+  } else if (is({256, 256})) {
+    set(0, kColQ, kColQ + 128, -1, 0);
+    set(1, kColP, kColR, 1, 1);
+    p.head_after = 1;
+  } else if (is({128}) || is({256})) {
+    set(0, w[0] == 128 ? kColP : kColQ, w[0] == 128 ? kColP : kColQ + 128, 0, 1);
+    p.head_after = 0;
+  } else {
+    DF3D_REQUIRE(false, DF3D_EUNSUPPORTED, "launch_conv_chain: no tensor-memory plan for this chain shape");
+  }
+  for (int i = 0; i < n; ++i)
+    DF3D_REQUIRE(p.st[i].hz_stage < 0 || p.st[i].hz_delta == 0 || p.st[i].hz_stage >= i, DF3D_EINVAL,
+                 "launch_conv_chain: ambiguous hazard in the tensor-memory plan");
   return DF3D_OK;
 }
 
@@ -517,40 +693,47 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
       st.epi_kind = kind;
     }
     st.aff_off = aff_floats;
-    aff_floats += 4 * st.n;
+    aff_floats += st.n * ((st.unit_scale ? 1 : 2) + (st.x_src == 2 ? 2 : 0));
     any_slab |= st.has_res != 0;
     any_res2 |= st.has_res2 != 0;
   }
-  // tensor-memory regions: head in P when it is 128 wide, else Q; 256-wide stages in Q; a 128-wide
-  // later stage takes the region the head does not use so that the next tile's head GEMM can overlap
-  // its epilogue
-  const int head_col = p.st[0].n == 128 ? kColP : kColQ;
-  p.st[0].acc_col = head_col;
-  for (int i = 1; i < p.n_chain; ++i) p.st[i].acc_col = p.st[i].n == 256 ? kColQ : (head_col == kColP ? kColQ : kColP);
-  // shared-memory budget
+  if (int e = plan_tmem(p)) return e;
+  // the slab producer walks tile by tile, stage by stage; the epilogue pulls the next head forward, which
+  // only keeps the same order when the head has no residual or is issued behind the last stage anyway
+  DF3D_REQUIRE(!p.st[0].has_res || p.head_after == p.n_chain - 1, DF3D_EUNSUPPORTED,
+               "launch_conv_chain: a head with a residual must be issued behind the last stage");
+  // shared-memory budget: constants, barriers, residual slabs, the rest is the operand ring
   p.aff_bytes = (aff_floats * 4 + 255) & ~255;
   p.slab_bytes = kUnitBytes + (any_res2 ? kUnitBytes / 4 : 0);
-  p.n_slabs = any_slab ? (p.taps == 9 ? 4 : 6) : 0;
-  const int fixed = 1024 + p.aff_bytes + kChainBarBytes + p.n_slabs * p.slab_bytes;
-  const int units = (kChainSmemLimit - fixed) / kUnitBytes;
-  p.n_w = p.n_chain > 1 ? (units >= 9 ? 3 : 2) : 0;
-  if (const char* env = getenv("DF3D_CHAIN_NS")) {  // profiling knobs: slab / weight-ring / head-ring depth
+  p.slot_bytes = (1 + (p.st[0].n >> 7)) * kUnitBytes;
+  if (p.slot_bytes < 2 * kUnitBytes) p.slot_bytes = 2 * kUnitBytes;
+  p.n_slabs = any_slab ? 4 : 0;
+  if (const char* env = getenv("DF3D_CHAIN_NS")) {  // profiling knob: residual slab depth
     const int v = atoi(env);
     if (any_slab && v >= 2 && v <= kMaxSlabs) p.n_slabs = v;
   }
-  if (const char* env = getenv("DF3D_CHAIN_NW")) {
-    const int v = atoi(env);
-    if (p.n_chain > 1 && v >= 2 && v <= kMaxW) p.n_w = v;
+  int fixed = 0;
+  for (;;) {
+    fixed = 1024 + p.aff_bytes + kChainBarBytes + p.n_slabs * p.slab_bytes;
+    p.n_m = (kChainSmemLimit - fixed) / p.slot_bytes;
+    if (p.n_m >= 3 || p.n_slabs <= 2) break;
+    --p.n_slabs;  // wide heads: trade slab depth for ring depth
   }
-  const int fixed2 = 1024 + p.aff_bytes + kChainBarBytes + p.n_slabs * p.slab_bytes;
-  p.n_m = (kChainSmemLimit - fixed2) / kUnitBytes - p.n_w;
   if (p.n_m > kMaxM) p.n_m = kMaxM;
-  if (const char* env = getenv("DF3D_CHAIN_NM")) {
+  if (const char* env = getenv("DF3D_CHAIN_NM")) {  // profiling knob: ring depth
     const int v = atoi(env);
-    if (v >= 3 && v < p.n_m) p.n_m = v;
+    if (v >= 2 && v < p.n_m) p.n_m = v;
   }
-  DF3D_REQUIRE(p.n_m >= 1 + (p.st[0].n >> 7) && p.n_w <= kMaxW, DF3D_EUNSUPPORTED, "launch_conv_chain: shared-memory budget too small");
-  const int smem = fixed2 + (p.n_m + p.n_w) * kUnitBytes;
+  DF3D_REQUIRE(p.n_m >= 2, DF3D_EUNSUPPORTED, "launch_conv_chain: shared-memory budget too small (%d ring slots)", p.n_m);
+  const int smem = fixed + p.n_m * p.slot_bytes;
+  // tile decode without divisions when the tile grid is a power of two (it is for every hourglass level)
+  auto log2_exact = [](int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return (1 << l) == v ? l : -1;
+  };
+  p.tx_shift = log2_exact(p.tiles_x);
+  p.ty_shift = log2_exact(p.tiles_y);
   const int grid = total < num_sms ? total : num_sms;
   conv_chain_kernel<<<grid, kChainThreads, smem, stream>>>(p);
   DF3D_LAUNCH_CHECK("conv_chain_kernel");

@@ -35,7 +35,10 @@ struct ChainStage {
   int unit_scale;  // scale1 is identically 1 (conv without a folded BatchNorm): the epilogue only adds shift1
   int has_res, has_res2;
   int x_src;     // operand handed to the next stage: 0 none (last stage), 1 raw, 2 act
-  int acc_col;   // TMEM column of this stage's accumulator (filled by launch_conv_chain)
+  // tensor-memory plan (filled by launch_conv_chain, see plan_tmem)
+  int col[2];    // accumulator columns of channels [0,128) and [128,256) (the latter unused for n = 128)
+  int hz_stage;  // epilogue that must have drained those columns before this stage is issued (-1: implied)
+  int hz_delta;  // ... of this tile (0) or of the previous one (1)
   int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)
   int epi_kind;  // specialised epilogue variant (filled by the launcher)
 };
@@ -50,14 +53,17 @@ struct ChainParams {
   int tw, th, nb;  // M tile = nb images x th rows x tw cols = 128 pixels
   int tiles_x, tiles_y, tiles_b;
   // shared-memory carve-up (filled by launch_conv_chain)
-  int n_m;         // head ring (A tiles + head weights), 16 KB units
-  int n_w;         // weight ring of the later stages, 16 KB units
+  int head_after;  // the head GEMM of the next tile is issued behind this stage (filled by launch_conv_chain)
+  int n_m;         // operand ring slots
+  int slot_bytes;  // 32 KB (48 KB for a 256-wide head): a head K block (A + weight half-tiles) or 32 KB of weights
+  int tx_shift, ty_shift;  // log2 of tiles_x / tiles_y when they are powers of two, else -1
   int n_slabs;     // residual slabs (TMA prefetch ring)
   int slab_bytes;  // 16384 (+4096 with a half-resolution residual)
   int aff_bytes;
   // profiling only (tools/chain_probe.cu): when non-null, CTA 0 records clock64() time stamps of its MMA
   // issuer ([0, 4096)) and of epilogue warps 4 and 8 ([4096, 8192), [8192, 12288))
   unsigned long long* dbg;
+  int dbg_exec;  // probe only: the MMA warp also waits for (and stamps) the completion of every stage >= 1
 };
 
 int conv_chain_configure();

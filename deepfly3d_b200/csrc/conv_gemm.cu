@@ -167,12 +167,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
+        mbar_wait_warp(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait_warp(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = desc_hi | (uint64_t)((a_addr(stage) >> 4) & 0x3FFFu);
           const uint64_t bdesc = desc_hi | (uint64_t)((b_addr(stage) >> 4) & 0x3FFFu);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       int nt, x0, y0, n0;
       decode_tile(tile, nt, x0, y0, n0);
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait_warp(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       } else {
 #pragma unroll 1
         for (int sl = 0; sl < kSlabs; ++sl) {
-          if (has_res) mbar_wait(rfull_bar(rslot), rphase);
+          if (has_res) mbar_wait_warp(rfull_bar(rslot), rphase);
           const uint32_t rbuf = res_base + rslot * res_slot_bytes + row_off;
           const uint32_t rbuf2 = res_base + rslot * res_slot_bytes + kSlabBytes + row2_off;
           const uint32_t raw_buf = raw_base + obuf * kSlabBytes + row_off;

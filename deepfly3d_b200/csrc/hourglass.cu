@@ -974,10 +974,10 @@ static int lanes_for(const df3d_hg_desc& d) {
 }
 
 static int fuse_for() {
-  // 2: 3x3-led conv chains; 1 (default, fastest measured so far): point-wise chains behind stand-alone
-  // 3x3 convs; 0: one launch per conv.  All three produce bit-identical results (tests/test_gpu_hourglass.py); the knob exists for
+  // 2 (default): 3x3-led conv chains; 1: point-wise chains behind stand-alone 3x3 convs; 0: one launch
+  // per conv.  All three produce bit-identical results (tests/test_gpu_hourglass.py); the knob exists for
   // that test and for profiling.
-  int f = 1;
+  int f = 2;
   if (const char* env = getenv("DF3D_HG_FUSE")) {
     const int v = atoi(env);
     if (v >= 0 && v <= 2) f = v;

@@ -58,6 +58,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Whole-warp wait with ONE polling lane: 32 lanes spinning on the same mbarrier serialise in the
+// shared-memory atomic unit and delay the arrivals everybody is waiting for.  The other lanes pick up
+// the acquired state through the warp barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+  }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {

@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
   p.tiles_y = H / th;
   p.tiles_b = B;
   p.dbg = dbg;
+  p.dbg_exec = argc > 4 ? atoi(argv[4]) : 0;
   int n = 0;
   auto stage = [&](int K, int N, size_t woff) -> ChainStage& {
     ChainStage& st = p.st[n++];
@@ -142,19 +143,27 @@ int main(int argc, char** argv) {
   }
   std::vector<unsigned long long> h(3 * 4096);
   CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
-  // MMA thread: per tile 3 + 2*(n-1) stamps; epilogue: per tile 2*n stamps
-  const int per_m = 3 + 2 * (n - 1), per_e = 2 * n;
-  const unsigned long long t0 = h[0];
-  printf("timeline of CTA 0 (clock cycles since the first tile start), tiles 20..25\n");
-  for (int t = 20; t < 26; ++t) {
-    const unsigned long long* m = &h[(size_t)t * per_m];
-    printf("tile %d MMA : start %llu  accfree +%llu  head_issued +%llu", t, m[0] - t0, m[1] - m[0], m[2] - m[1]);
-    for (int i = 1; i < n; ++i) printf(" | %s: xready +%llu issued +%llu", names[i], m[1 + 2 * i] - m[2 * i], m[2 + 2 * i] - m[1 + 2 * i]);
-    printf("  => tile total %llu\n", (&h[(size_t)(t + 1) * per_m])[0] - m[0]);
-    for (int g = 0; g < 2; ++g) {
-      const unsigned long long* e = &h[4096 * (1 + g) + (size_t)t * per_e];
-      printf("        EPI%d:", g);
-      for (int i = 0; i < n; ++i) printf(" %s ready@%llu busy %llu |", names[i], e[2 * i] - t0, e[2 * i + 1] - e[2 * i]);
+  // MMA warp stamps: head(0) start/issued, then per tile: for each stage i >= 1 (ready, issued), with the next
+  // head's (start, issued) behind stage head_after.  Epilogue stamps: (ready, done) per stage in its own order.
+  const int per = 2 * n;  // stamps per tile in steady state, both roles
+  const int per_m = per + (p.dbg_exec ? n - 1 : 0);
+  printf("MMA warp, tiles 20..23: deltas in clock cycles between consecutive stamps (period = %d stamps per tile)\n", per);
+  for (int t = 20; t < 24; ++t) {
+    printf("  tile %d:", t);
+    for (int j = 0; j < per_m; ++j) {
+      const size_t k = 2 + (size_t)t * per_m + j;
+      printf(" %llu", h[k] - h[k - 1]);
+    }
+    printf("   => %llu per tile\n", h[2 + (size_t)(t + 1) * per_m] - h[2 + (size_t)t * per_m]);
+  }
+  for (int g = 0; g < 2; ++g) {
+    printf("epilogue group %d, tiles 20..23: (loop overhead, barrier wait, busy) per stage in program order\n", g);
+    for (int t = 20; t < 24; ++t) {
+      printf("  tile %d:", t);
+      for (int j = 0; j < n; ++j) {
+        const size_t k = 4096 * (1 + g) + 3 + (size_t)t * 3 * n + 3 * j;
+        printf(" (%llu, %llu, %llu)", h[k] - h[k - 1], h[k + 1] - h[k], h[k + 2] - h[k + 1]);
+      }
       printf("\n");
     }
   }
