@@ -322,7 +322,7 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host_images.numel()) * world,
                 "d2h_bytes_per_step": int(host_x3d.numel() * 8 + host_cam.numel() * 8)},
         "gpu_launches": int(pipe.launches(n_img)) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<BN> (tcgen05 implicit-GEMM conv, all instantiations)",
+        "roofline": {"bound": "tensor", "kernel": "conv_chain_kernel + conv_gemm_kernel<BN> (tcgen05 implicit-GEMM convs and conv chains)",
                      "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / pk["tf_sustained"], "peak_source": f"bf16_tflops_sustained, of {pk['which']}",
                      "launches_per_step": conv["conv_launches"] / args.steps,

@@ -113,6 +113,48 @@ stem_im2col_kernel(const void* __restrict__ img, int dtype, const uint8_t* __res
   }
 }
 
+// Gray fast path of the stem: the three input planes are the same image (x/255 - mean with one
+// common mean), so the 7x7x3 conv is a 7x7x1 conv with the weights summed over the input channel and
+// the patch matrix has 49 (padded to 64) columns instead of 147 (192).  One CTA = 32 consecutive
+// output pixels of one output row, one 16-byte chunk (8 patch columns) per thread.
+__constant__ uint8_t c_gray_tap[64];  // patch column -> ky * 16 + kx (0xff for the 15 padding columns)
+
+__global__ void __launch_bounds__(256)
+stem_im2col_gray_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ flip, int B, int H, int W, float mean,
+                        __nv_bfloat16* __restrict__ out) {
+  __shared__ float win[7][kStemCols + 3];
+  const int Ho = H / 2, Wo = W / 2;
+  const int segs = Wo / kStemPix;
+  int blk = blockIdx.x;
+  const int seg = blk % segs;
+  blk /= segs;
+  const int oy = blk % Ho;
+  const int b = blk / Ho;
+  const int ox0 = seg * kStemPix;
+  const bool fl = flip ? (flip[b] != 0) : false;
+  for (int i = threadIdx.x; i < 7 * kStemCols; i += 256) {
+    const int ky = i / kStemCols, cx = i - ky * kStemCols;
+    const int iy = 2 * oy + ky - 3;
+    int ix = 2 * ox0 + cx - 3;
+    float v = 0.0f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (fl) ix = W - 1 - ix;
+      v = (float)img[((size_t)b * H + iy) * W + ix] / 255.0f - mean;
+    }
+    win[ky][cx] = v;
+  }
+  __syncthreads();
+  const int px = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t t = c_gray_tap[chunk * 8 + e];
+    v[e] = t == 0xffu ? 0.0f : win[t >> 4][2 * px + (t & 15u)];
+  }
+  __nv_bfloat16* row = out + (((size_t)b * Ho + oy) * Wo + ox0) * kStemKGray;
+  *reinterpret_cast<uint4*>(row + (size_t)threadIdx.x * 8) = pack8(v);
+}
+
 __global__ void __launch_bounds__(256)
 maxpool_bn_relu_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int C,
                        const float* __restrict__ scale, const float* __restrict__ shift,
@@ -157,6 +199,28 @@ int launch_stem_im2col(const void* img, int dtype, const uint8_t* flip, int B, i
   DF3D_REQUIRE(blocks < (1ll << 31), DF3D_EUNSUPPORTED, "stem_im2col: too many blocks");
   stem_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(img, dtype, flip, B, H, W, mean[0], mean[1], mean[2], out);
   DF3D_LAUNCH_CHECK("stem_im2col_kernel");
+  return DF3D_OK;
+}
+
+int launch_stem_im2col_gray(const uint8_t* img, const uint8_t* flip, int B, int H, int W, float mean, __nv_bfloat16* out,
+                            cudaStream_t s) {
+  if (B == 0) return DF3D_OK;
+  DF3D_REQUIRE((W / 2) % kStemPix == 0, DF3D_EUNSUPPORTED, "stem_im2col: input width must be a multiple of %d", 2 * kStemPix);
+  static bool table_ready = false;  // same table for every device / handle; uploaded on first use per process
+  static int table_device = -1;
+  int dev = 0;
+  DF3D_CUDA(cudaGetDevice(&dev));
+  if (!table_ready || table_device != dev) {
+    uint8_t tap[64];
+    for (int k = 0; k < 64; ++k) tap[k] = k < 49 ? (uint8_t)((k / 7) * 16 + (k % 7)) : (uint8_t)0xff;
+    DF3D_CUDA(cudaMemcpyToSymbol(c_gray_tap, tap, sizeof(tap)));
+    table_ready = true;
+    table_device = dev;
+  }
+  const long long blocks = (long long)B * (H / 2) * ((W / 2) / kStemPix);
+  DF3D_REQUIRE(blocks < (1ll << 31), DF3D_EUNSUPPORTED, "stem_im2col: too many blocks");
+  stem_im2col_gray_kernel<<<(unsigned)blocks, 256, 0, s>>>(img, flip, B, H, W, mean, out);
+  DF3D_LAUNCH_CHECK("stem_im2col_gray_kernel");
   return DF3D_OK;
 }
 

@@ -164,10 +164,11 @@ struct Arena {
   }
 };
 
-enum OpKind { OP_IM2COL, OP_CONV, OP_CHAIN, OP_POOL, OP_ARGMAX };
+enum OpKind { OP_IM2COL, OP_IM2COL_GRAY, OP_CONV, OP_CHAIN, OP_POOL, OP_ARGMAX };
 
 struct Op {
   OpKind kind;
+  int variant = 0;  // stem only: 0 always, 1 three-plane path, 2 gray fast path (uint8 input, one common mean)
   // conv / chain
   ConvParams conv;
   ChainParams chain;
@@ -313,6 +314,24 @@ struct Emitter {
         for (int ci = 0; ci < 3; ++ci)
           for (int t = 0; t < 49; ++t)
             hg->wblob[o + (size_t)co * K + (size_t)t * 3 + ci] = f2bf(c.w[((size_t)co * 3 + ci) * 49 + t]);
+    }
+    return o;
+  }
+
+  // gray fast path: the three input planes are identical, so the weights are summed over the input
+  // channel (fp32) before the bf16 rounding; K index = ky*7 + kx, padded to 64
+  size_t pack_stem_gray(const Convp& c) {
+    const size_t K = kStemKGray;
+    size_t o = w_cursor;
+    w_cursor += (size_t)c.cout * K;
+    if (dry) {
+      hg->wblob.resize(w_cursor, 0);
+      for (int co = 0; co < c.cout; ++co)
+        for (int t = 0; t < 49; ++t) {
+          float sum = 0.0f;
+          for (int ci = 0; ci < 3; ++ci) sum += c.w[((size_t)co * 3 + ci) * 49 + t];
+          hg->wblob[o + (size_t)co * K + t] = f2bf(sum);
+        }
     }
     return o;
   }
@@ -836,6 +855,7 @@ struct Emitter {
       Op op;
       op.kind = OP_IM2COL;
       op.out0 = ptr(col);
+      op.variant = 1;
       hg->ops.push_back(op);
     }
     size_t w0 = pack_stem(net.conv1);
@@ -843,6 +863,21 @@ struct Emitter {
     Affine a0n = bn_affine(net.layer1.bn1, kInplanes);
     Tensor x = talloc(H2, W2, kInplanes), xa = talloc(H2, W2, kInplanes);
     conv(col, w0, 1, kStemKPadCols, kInplanes, 64, a0, true, nullptr, &x, &a0n, &xa, nullptr, fpp(net.conv1));
+    if (!dry && !err) hg->ops.back().variant = 1;
+    // gray fast path of the same two launches (chosen per call in df3d_hg_forward_argmax)
+    Tensor colg = col;
+    colg.C = kStemKGray;
+    n_ops += 1;
+    if (!dry && !err) {
+      Op op;
+      op.kind = OP_IM2COL_GRAY;
+      op.out0 = ptr(colg);
+      op.variant = 2;
+      hg->ops.push_back(op);
+    }
+    size_t w0g = pack_stem_gray(net.conv1);
+    conv(colg, w0g, 1, kStemKGray, kInplanes, 64, a0, true, nullptr, &x, &a0n, &xa, nullptr, fpp(net.conv1));
+    if (!dry && !err) hg->ops.back().variant = 2;
     tfree(col);
 
     Tensor y1, none;
@@ -1050,7 +1085,7 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
   e.run();
   hg->lane_bytes = (e.arena.top + 1023) & ~size_t(1023);
   hg->ws_bytes = (size_t)hg->n_lanes * hg->lane_bytes + 1024;
-  hg->ops_per_chunk = e.n_ops;
+  hg->ops_per_chunk = e.n_ops - 2;  // of the two stem variants (im2col + GEMM each) one runs
   cudaError_t ce = cudaMalloc(&hg->d_w, hg->wblob.size() * sizeof(uint16_t));
   if (ce == cudaSuccess && hg->n_lanes > 1) ce = cudaEventCreateWithFlags(&hg->fork_ev, cudaEventDisableTiming);
   for (int l = 1; l < hg->n_lanes && ce == cudaSuccess; ++l) {
@@ -1148,6 +1183,8 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
   const size_t heat_elems = (size_t)hg->Hh * hg->Wh * kHeatPad;
 
   const size_t n_ops = hg->ops.size();
+  // gray fast path of the stem: uint8 gray input replicated to three planes with one common mean
+  const bool gray = dtype == 0 && hg->mean[0] == hg->mean[1] && hg->mean[1] == hg->mean[2] && !getenv("DF3D_HG_NO_GRAY");
   const std::vector<Piece> pieces = cut_batch(hg, B);
   if (hg->timing) {
     while (hg->events.size() < pieces.size() * n_ops * 2) {
@@ -1171,7 +1208,18 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
     for (size_t oi = 0; oi < n_ops; ++oi) {
       const Op& op = ops[oi];
       if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi], ls));
+      if (op.variant != 0 && op.variant != (gray ? 2 : 1)) {  // the other stem variant
+        if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi + 1], ls));
+        continue;
+      }
       switch (op.kind) {
+        case OP_IM2COL_GRAY: {
+          const uint8_t* img = static_cast<const uint8_t*>(images_dev) + (size_t)c0 * img_stride;
+          if (int e = launch_stem_im2col_gray(img, flip_dev ? flip_dev + c0 : nullptr, bc, d.in_h, d.in_w, hg->mean[0],
+                                              reinterpret_cast<__nv_bfloat16*>(op.out0), ls))
+            return e;
+          break;
+        }
         case OP_IM2COL: {
           const char* img = static_cast<const char*>(images_dev) + (size_t)c0 * img_stride;
           if (int e = launch_stem_im2col(img, dtype, flip_dev ? flip_dev + c0 : nullptr, bc, d.in_h, d.in_w, hg->mean,
@@ -1313,6 +1361,9 @@ extern "C" int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, doub
   } else if (op.kind == OP_POOL) {
     bpi = (double)op.H * op.W * op.C * 2.0 * 1.5;
     snprintf(desc, desc_len, "maxpool+bn  %4dx%-4d c=%3d", op.H, op.W, op.C);
+  } else if (op.kind == OP_IM2COL_GRAY) {
+    bpi = (double)hg->desc.in_h * hg->desc.in_w + (double)hg->desc.in_h * hg->desc.in_w / 4 * kStemKGray * 2.0;
+    snprintf(desc, desc_len, "stem im2col (gray)");
   } else if (op.kind == OP_IM2COL) {
     bpi = (double)hg->desc.in_h * hg->desc.in_w + (double)hg->desc.in_h * hg->desc.in_w / 4 * kStemKPadCols * 2.0;
     snprintf(desc, desc_len, "stem im2col");

@@ -99,11 +99,20 @@ class HourglassNet(nn.Module):
         self.fc_ = nn.ModuleList([nn.Conv2d(ch, ch, 1, bias=True) for _ in range(num_stacks - 1)])
         self.score_ = nn.ModuleList([nn.Conv2d(num_classes, ch, 1, bias=True) for _ in range(num_stacks - 1)])
 
-    def forward(self, x, emulate_bf16=False):
+    def forward(self, x, emulate_bf16=False, gray_fold=None):
+        """gray_fold (emulation only): the CUDA path takes uint8 gray images whose three input planes are
+        identical and folds the stem weights over the input channel (fp32 sum, one bf16 rounding);
+        None = do the same whenever the three planes of `x` are identical."""
         rnd = _bf16 if emulate_bf16 else (lambda t: t)
         wq = (lambda c: _bf16(c.weight)) if emulate_bf16 else (lambda c: c.weight)
         x = rnd(x)
-        x = rnd(F.relu(self.bn1(F.conv2d(x, wq(self.conv1), self.conv1.bias, stride=2, padding=3))))
+        if gray_fold is None:
+            gray_fold = bool(torch.equal(x[:, 0], x[:, 1]) and torch.equal(x[:, 0], x[:, 2]))
+        if emulate_bf16 and gray_fold:
+            w1 = _bf16(self.conv1.weight.sum(dim=1, keepdim=True))
+            x = rnd(F.relu(self.bn1(F.conv2d(x[:, :1], w1, self.conv1.bias, stride=2, padding=3))))
+        else:
+            x = rnd(F.relu(self.bn1(F.conv2d(x, wq(self.conv1), self.conv1.bias, stride=2, padding=3))))
         x = self.layer1[0](x, rnd, wq)
         x = F.max_pool2d(x, 2, stride=2)
         x = self.layer2[0](x, rnd, wq)

@@ -41,7 +41,7 @@ def _compare(hgmod, stacks, H, W, B, seed, flip=None, float_input=False):
         idx, conf, heat = eng.forward(img.cuda(), flip=None if fl is None else fl.cuda(), return_heatmap=True)
     torch.cuda.synchronize()
     with torch.no_grad():
-        ref = model(x, emulate_bf16=True)[-1]                       # (B,K,Hh,Wh) fp32
+        ref = model(x, emulate_bf16=True, gray_fold=not float_input)[-1]   # (B,K,Hh,Wh) fp32
     got = heat[..., :19].permute(0, 3, 1, 2).cpu()
     assert torch.isfinite(got).all()
     rng_ = (ref.max() - ref.min()).item()

@@ -15,11 +15,11 @@ if [ "$1" = "ncu" ]; then
   echo "ncu launches exit=$? lines=$(wc -l < gpurun_out/launches.csv)" | tee -a gpurun_out/summary.txt
   # full captures (small batch: ncu replays each launch ~40x): a few conv launches of each shape class + the 2D->3D tail
   timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --set full --clock-control none --import-source on \
-      -k regex:conv_gemm_kernel -s 4 -c 12 -f -o gpurun_out/prof_conv \
+      -k regex:conv_ -s 8 -c 14 -f -o gpurun_out/prof_conv \
       python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full conv exit=$?" | tee -a gpurun_out/summary.txt
   timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --set full --clock-control none --import-source on \
-      -k regex:'argmax|pack_points|triangulate|ba_linearize|ba_solve|ba_evaluate|maxpool|im2col' -c 12 -f -o gpurun_out/prof_tail \
+      -k regex:'argmax|pack_points|triangulate|ba_linearize|ba_solve|ba_evaluate' -c 12 -f -o gpurun_out/prof_tail \
       python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_tail.log 2>&1
   echo "ncu full tail exit=$?" | tee -a gpurun_out/summary.txt
 fi
