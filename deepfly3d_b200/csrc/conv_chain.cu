@@ -369,19 +369,41 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
     int di = 0;
 
+    // Ring consumption with the barrier latency taken off the issue path: the readiness of the NEXT slot is
+    // probed (mbarrier.try_wait) before the MMAs of the current one are issued, so the probe's round trip
+    // overlaps the tensor work instead of sitting between two groups of MMAs.
+    bool ring_ready = false;  // outcome of the early probe of slot `mu`
+    auto ring_wait = [&]() {
+      if (!ring_ready) mbar_wait(mfull(mu), mph);
+      tc_fence_after();
+    };
+    auto ring_probe_next = [&]() {
+      uint32_t nu = mu + 1, nph = mph;
+      if (nu == n_m) {
+        nu = 0;
+        nph ^= 1u;
+      }
+      ring_ready = mbar_try_wait(mfull(nu), nph);
+    };
+    auto ring_advance = [&]() {
+      if (++mu == n_m) {
+        mu = 0;
+        mph ^= 1u;
+      }
+    };
+
     // head GEMM of local tile number `t` (A and B from shared memory)
     auto issue_head = [&](int t) {
       if (dbg && di < 4000) dbg[di++] = clock64();  // [head start]
-      if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait_warp(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
-      tc_fence_after();
+      if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
 #pragma unroll 1
       for (int kb = 0; kb < kb0; ++kb) {
-        mbar_wait_warp(mfull(mu), mph);
-        tc_fence_after();
+        ring_wait();
         const uint32_t a_addr = m_base + mu * slot_bytes;
         const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
         const uint64_t b0 = desc_hi | (uint64_t)(((a_addr + kUnitBytes) >> 4) & 0x3FFFu);
         const uint64_t b1 = desc_hi | (uint64_t)(((a_addr + 2 * kUnitBytes) >> 4) & 0x3FFFu);
+        ring_probe_next();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
@@ -392,14 +414,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           umma_commit(mempty(mu));  // frees the ring stage once these MMAs retire
         }
-        __syncwarp();
-        if (++mu == n_m) {
-          mu = 0;
-          mph ^= 1u;
-        }
+        ring_advance();
       }
       if (elect_one()) umma_commit(accfull(0));
-      __syncwarp();
       if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
     };
 
@@ -412,18 +429,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const uint32_t c0 = tmem_base + (uint32_t)L.col0, c1 = tmem_base + (uint32_t)L.col1;
       const uint32_t x0c = tmem_base + (uint32_t)Lp.col0, x1c = tmem_base + (uint32_t)Lp.col1;
       const int hz = L.hz, hzd = L.hzd;
-      mbar_wait_warp(epidone(i - 1), par);  // operand of this stage is complete in tensor memory
-      if (hz >= 0 && t - hzd >= 0) mbar_wait_warp(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
+      mbar_wait(epidone(i - 1), par);  // operand of this stage is complete in tensor memory
+      if (hz >= 0 && t - hzd >= 0) mbar_wait(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
       tc_fence_after();
       if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
       const int slots = (kbn * nh) >> 1;
 #pragma unroll 1
       for (int sl = 0; sl < slots; ++sl) {
-        mbar_wait_warp(mfull(mu), mph);
-        tc_fence_after();
+        ring_wait();
         const uint32_t b_addr = m_base + mu * slot_bytes;
         const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
         const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kUnitBytes) >> 4) & 0x3FFFu);
+        ring_probe_next();
         if (elect_one()) {
           if (nh == 2) {  // K block sl, both output halves
             const uint32_t xa = ((sl >> 1) ? x1c : x0c) + (sl & 1) * 64;
@@ -440,17 +457,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           umma_commit(mempty(mu));
         }
-        __syncwarp();
-        if (++mu == n_m) {
-          mu = 0;
-          mph ^= 1u;
-        }
+        ring_advance();
       }
       if (elect_one()) umma_commit(accfull(i));  // accumulator ready; the consumed operand may be overwritten
-      __syncwarp();
       if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
       if (p.dbg_exec) {  // probe only: how long until the accumulator is complete (serialises this warp)
-        mbar_wait_warp(accfull(i), par);
+        mbar_wait(accfull(i), par);
         if (dbg && di < 4000) dbg[di++] = clock64();
       }
     };
