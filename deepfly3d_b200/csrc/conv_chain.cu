@@ -38,6 +38,8 @@ constexpr int kChainThreads = 384;  // warpgroup 0: producer / MMA / slab produc
 constexpr int kEpiWarp0c = 4;
 constexpr int kUnitBytes = 16384;       // 128 rows x 64 bf16: one A tile or one 128-row weight half-tile
 constexpr int kMaxM = 8, kMaxSlabs = 8;  // ring slots, residual slabs
+constexpr int kHaloPitch = 10;               // halo row = 8 tile pixels + one on each side
+constexpr int kHaloBytes = 18 * kHaloPitch * 128;  // one 64-channel half of the halo of an 8 x 16 tile (45 KB)
 constexpr int kColP = 0, kColQ = 128, kColR = 384;
 constexpr int kChainSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int kChainBarBytes = 1024;  // barriers, TMEM slot, StageLite table
@@ -165,7 +167,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   // half-tiles) or 32 KB of later-stage weights per slot
   const uint32_t slot_bytes = (uint32_t)p.slot_bytes;
   const uint32_t m_base = smem_base;
-  const uint32_t s_base = m_base + (uint32_t)p.n_m * slot_bytes;
+  // halo mode (3x3 head on maps of at least 16 x 8): the head's activations are not streamed per tap; the
+  // (th+2) x (tw+2) pixel halo of the tile is loaded once per 64-channel half and the nine taps are
+  // row-shifted views of it (see issue_head); the ring then carries the head's weights only
+  const uint32_t halo_base = m_base + (uint32_t)p.n_m * slot_bytes;
+  const uint32_t s_base = halo_base + (p.halo ? 2u * kHaloBytes : 0u);
   const uint32_t aff_base = s_base + (uint32_t)p.n_slabs * (uint32_t)p.slab_bytes;
   const uint32_t bar_base = aff_base + (uint32_t)p.aff_bytes;
   auto mfull = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -174,7 +180,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   auto sempty = [&](uint32_t s) { return bar_base + 8u * (2 * kMaxM + kMaxSlabs + s); };
   auto accfull = [&](uint32_t i) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + i); };
   auto epidone = [&](uint32_t i) { return bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + kMaxChain + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
+  const uint32_t hfull = bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
+  const uint32_t hempty = hfull + 8u;
+  const uint32_t tmem_slot = hfull + 16u;
   const StageLite* const lite0 = reinterpret_cast<const StageLite*>(sm + (bar_base - smem_base) + 8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 64);
   auto lite = [&](int i) -> const StageLite& { return *reinterpret_cast<const StageLite*>(reinterpret_cast<const uint8_t*>(lite0) + i * kLiteStride); };
 
@@ -202,6 +210,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_init(accfull(i), 1);
       mbar_init(epidone(i), 8);  // one arrive per epilogue warp
     }
+    mbar_init(hfull, 1);
+    mbar_init(hempty, 1);
+    if (p.halo) prefetch_tensormap(&p.tmHalo);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -277,9 +288,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           ph ^= 1u;
         }
       };
+      uint32_t heads = 0;
       auto load_head = [&](int tile) {
         int x0, y0, n0;
         decode_tile(tile, x0, y0, n0);
+        if (p.halo) {  // the halo once, then one 32 KB slot of weights per tap (both 64-channel halves)
+          mbar_wait(hempty, (heads & 1u) ^ 1u);
+          mbar_arrive_expect_tx(hfull, 2u * kHaloBytes);
+          tma_load_4d(halo_base, &p.tmHalo, hfull, 0, x0 - 1, y0 - 1, n0);
+          tma_load_4d(halo_base + kHaloBytes, &p.tmHalo, hfull, 64, x0 - 1, y0 - 1, n0);
+          ++heads;
+          for (int tap9 = 0; tap9 < 9; ++tap9) {
+            const uint32_t dst = acquire(2 * kUnitBytes);
+            tma_load_2d(dst, &p.st[0].tmB, mfull(u), (2 * tap9) * 64, 0);
+            tma_load_2d(dst + kUnitBytes, &p.st[0].tmB, mfull(u), (2 * tap9 + 1) * 64, 0);
+            advance();
+          }
+          return;
+        }
         int tap = 0, kc = 0;
         for (int kb = 0; kb < kb0; ++kb) {
           int dx = 0, dy = 0;
@@ -393,9 +419,46 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     };
 
     // head GEMM of local tile number `t` (A and B from shared memory)
+    const uint64_t desc_halo = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32);  // group pitch
+    uint32_t heads = 0;
     auto issue_head = [&](int t) {
       if (dbg && di < 4000) dbg[di++] = clock64();  // [head start]
       if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
+      if (p.halo) {
+        // A operand of tap (dy, dx) = the halo rows shifted by dy*10 + dx: pixel (r, c) of the 8-wide tile is
+        // halo row (r+dy)*10 + (c+dx), i.e. 8-row groups 1280 B apart starting at a row offset.  The 128B
+        // swizzle is a function of the absolute shared-memory address (what TMA wrote), so the shifted
+        // start needs no descriptor base_offset (measured: bit-identical to nine separate TMA boxes).
+        mbar_wait(hfull, heads & 1u);
+        ++heads;
+        tc_fence_after();
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          ring_wait();
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t a_addr = halo_base + (uint32_t)(dy * kHaloPitch + dx) * 128u;
+          const uint64_t a0 = desc_halo | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+          const uint64_t a1 = desc_halo | (uint64_t)(((a_addr + kHaloBytes) >> 4) & 0x3FFFu);
+          const uint32_t b_addr = m_base + mu * slot_bytes;
+          const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+          const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kUnitBytes) >> 4) & 0x3FFFu);
+          ring_probe_next();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0, a0 + 2u * k, b0 + 2u * k, idesc, (tap | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0, a1 + 2u * k, b1 + 2u * k, idesc, 1u);
+            umma_commit(mempty(mu));
+          }
+          ring_advance();
+        }
+        if (elect_one()) {
+          umma_commit(hempty);  // the halo may be overwritten once these MMAs retire
+          umma_commit(accfull(0));
+        }
+        if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
+        return;
+      }
 #pragma unroll 1
       for (int kb = 0; kb < kb0; ++kb) {
         ring_wait();
@@ -719,14 +782,18 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
   p.slab_bytes = kUnitBytes + (any_res2 ? kUnitBytes / 4 : 0);
   p.slot_bytes = (1 + (p.st[0].n >> 7)) * kUnitBytes;
   if (p.slot_bytes < 2 * kUnitBytes) p.slot_bytes = 2 * kUnitBytes;
-  p.n_slabs = any_slab ? 4 : 0;
+  if (p.halo) {
+    DF3D_REQUIRE(p.taps == 9 && p.kc_per_tap == 2 && p.st[0].n == 128 && p.tw == 8 && p.th == 16 && p.nb == 1, DF3D_EINVAL,
+                 "launch_conv_chain: halo mode needs a 3x3 head with 128 input and output channels on 8 x 16 tiles");
+  }
+  p.n_slabs = any_slab ? (p.halo ? 3 : 4) : 0;
   if (const char* env = getenv("DF3D_CHAIN_NS")) {  // profiling knob: residual slab depth
     const int v = atoi(env);
     if (any_slab && v >= 2 && v <= kMaxSlabs) p.n_slabs = v;
   }
   int fixed = 0;
   for (;;) {
-    fixed = 1024 + p.aff_bytes + kChainBarBytes + p.n_slabs * p.slab_bytes;
+    fixed = 1024 + p.aff_bytes + kChainBarBytes + p.n_slabs * p.slab_bytes + (p.halo ? 2 * kHaloBytes : 0);
     p.n_m = (kChainSmemLimit - fixed) / p.slot_bytes;
     if (p.n_m >= 3 || p.n_slabs <= 2) break;
     --p.n_slabs;  // wide heads: trade slab depth for ring depth

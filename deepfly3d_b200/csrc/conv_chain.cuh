@@ -45,8 +45,10 @@ struct ChainStage {
 
 struct ChainParams {
   CUtensorMap tmA;  // head activations, 4-D (C, W, H, N), box (64, tw, th, nb), SWIZZLE_128B, OOB = 0
+  CUtensorMap tmHalo;  // halo mode: box (64, tw + 2, th + 2, 1) of the same tensor (see conv_chain.cu)
   ChainStage st[kMaxChain];
   int n_chain;
+  int halo;        // != 0: the 3x3 head reads nine row-shifted views of one halo tile instead of nine TMA boxes
   int taps;        // head: 1 or 9
   int kc_per_tap;  // head: Cin / 64
   int H, W, B;

@@ -508,8 +508,20 @@ struct Emitter {
     memset(&p, 0, sizeof(p));
     int tw, th, nb;
     tile_geometry(in.H, in.W, &tw, &th, &nb);
+    // halo mode of the chain kernel: 8 x 16 tiles whose 3x3 head reads row-shifted views of one halo tile
+    const bool halo = taps == 9 && CinPad == 128 && sp[0].N == 128 && in.H >= 16 && in.W >= 8 && in.H % 16 == 0 &&
+                      in.W % 8 == 0 && !getenv("DF3D_HG_NO_HALO");
+    if (halo) {
+      tw = 8;
+      th = 16;
+      nb = 1;
+    }
     op.nb = nb;
     if ((err = make_tmap_act(&p.tmA, ptr(in), in.C, in.W, in.H, B, tw, th, nb))) return;
+    if (halo) {
+      p.halo = 1;
+      if ((err = make_tmap_box(&p.tmHalo, ptr(in), in.C, in.W, in.H, B, tw + 2, th + 2, 1))) return;
+    }
     p.n_chain = n;
     p.taps = taps;
     p.kc_per_tap = CinPad / 64;

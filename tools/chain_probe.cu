@@ -52,8 +52,13 @@ int main(int argc, char** argv) {
 
   ChainParams p;
   memset(&p, 0, sizeof(p));
-  const int tw = 16, th = 8, nb = 1;
+  const int halo = (argc > 5 ? atoi(argv[5]) : 1) && taps == 9;
+  const int tw = halo ? 8 : 16, th = halo ? 16 : 8, nb = 1;
   int rc = make_tmap_act(&p.tmA, t1, 128, W, H, B, tw, th, nb);
+  if (halo) {
+    p.halo = 1;
+    rc |= make_tmap_box(&p.tmHalo, t1, 128, W, H, B, tw + 2, th + 2, 1);
+  }
   p.taps = taps;
   p.kc_per_tap = 2;
   p.H = H;
