@@ -1,10 +1,16 @@
 // tcgen05 convolution-chain kernel (see conv_chain.cuh).
 //
-// One persistent CTA per SM, 12 warps, 128-pixel tiles:
+// One persistent CTA per SM, 12 warps, 128-pixel tiles; the two SMs of a TPC work as a CTA PAIR
+// (cluster of 2, tcgen05 cta_group::2): every MMA is M = 256 -- 128 pixels of each CTA's own tile -- by
+// N = 128, and the weights, the operand the two tiles share, are split between the CTAs: each CTA fetches
+// and holds only 64 of the 128 weight rows of an MMA.  Measured on B200 (tools/chain_probe, tools/l2_probe):
+// the single-CTA form is bound by the 128 B/clk shared-memory port (an M128 x N128 SS MMA reads 8 KB per
+// 64 clocks by itself, plus the TMA writes of the weight stream); the pair halves the weight traffic.
 //   warp 0  TMA producer of the operand ring, in the MMA warp's issue order: per 64-wide K block of the head
 //           one A tile (a 4-D box per tap and channel block; the 3x3 halo is the TMA's out-of-bounds
-//           zero fill) + the head's weight half-tiles; per later stage 32 KB slots of weights
-//   warp 1  MMA issuer + TMEM owner (warp-uniform loop, one elected lane issues)
+//           zero fill) + this CTA's half of the head's weights; per later stage 16 KB slots of weights.
+//           Completion is signalled on the LEADER CTA's barriers (the leader issues the MMAs of the pair)
+//   warp 1  leader CTA (rank 0): MMA issuer; both CTAs: TMEM owner (warp-uniform loop, one elected lane issues)
 //   warp 2  TMA producer of the residual slabs (64 channels x 128 pixels, + the half-resolution slab
 //           of the up-sample branch), a ring that prefetches across stages and tiles
 //   warp 3  idle
@@ -13,7 +19,8 @@
 //
 // Stage i of a tile:
 //   MMA      D(acc_i) = A_i * W_i^T;  A_0 from shared memory (TMA), A_i (i >= 1) from tensor memory
-//   epilogue tcgen05.ld acc_i -> scale/shift (+ residuals) -> ReLU / bf16 rounding
+//   epilogue (each CTA for its own tile, out of its own tensor memory; "done" is counted on the leader's
+//            barrier: 8 warps of each CTA) tcgen05.ld acc_i -> scale/shift (+ residuals) -> ReLU / bf16 rounding
 //            -> optional bf16 store straight from registers (each thread owns one pixel row: 64
 //               contiguous bytes per 32 channels = two full-sector 256-bit stores)
 //            -> optional next-BatchNorm + ReLU -> tcgen05.st of the bf16 operand of stage i+1 IN PLACE
@@ -25,6 +32,7 @@
 // (the stage with the longest epilogue), so the tensor pipe works on the next 3x3 conv while the
 // epilogue warps apply residual / BatchNorm / stores of this one.
 #include <cstdlib>
+#include <cstring>
 #include <initializer_list>
 
 #include "conv_chain.cuh"
@@ -36,8 +44,9 @@ using namespace sm100;
 
 constexpr int kChainThreads = 384;  // warpgroup 0: producer / MMA / slab producer / idle; warpgroups 1, 2: epilogue
 constexpr int kEpiWarp0c = 4;
-constexpr int kUnitBytes = 16384;       // 128 rows x 64 bf16: one A tile or one 128-row weight half-tile
-constexpr int kMaxM = 8, kMaxSlabs = 8;  // ring slots, residual slabs
+constexpr int kUnitBytes = 16384;       // 128 rows x 64 bf16: one A tile
+constexpr int kSubBytes = 8192;         // 64 rows x 64 bf16: this CTA's half of the weights of one N = 128, K = 64 block
+constexpr int kMaxM = 12, kMaxSlabs = 8;  // ring slots, residual slabs
 constexpr int kHaloPitch = 10;               // halo row = 8 tile pixels + one on each side
 constexpr int kHaloBytes = 18 * kHaloPitch * 128;  // one 64-channel half of the halo of an 8 x 16 tile (45 KB)
 constexpr int kColP = 0, kColQ = 128, kColR = 384;
@@ -190,6 +199,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int n_chain = p.n_chain;
   const int head_after = p.head_after;
+  // CTA pair: rank 0 (the leader) issues every MMA; pair-tile pt = tiles 2 pt (leader) and 2 pt + 1 (peer); a
+  // tile past the end is a phantom (its loads are out of bounds = zeros, its stores are skipped)
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pt = (total_tiles + 1) >> 1;
+  const int pt0 = (int)(blockIdx.x >> 1), pstride = (int)(gridDim.x >> 1);
+  // the leader's copies of the barriers both CTAs signal (shared::cluster addresses)
+  const uint32_t lead_bar = mapa_cluster(bar_base, 0);
+  auto mfull_l = [&](uint32_t s) { return lead_bar + 8u * s; };
+  auto epidone_l = [&](uint32_t i) { return lead_bar + 8u * (2 * kMaxM + 2 * kMaxSlabs + kMaxChain + i); };
+  const uint32_t hfull_l = lead_bar + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA);
@@ -208,14 +228,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
     for (int i = 0; i < n_chain; ++i) {
       mbar_init(accfull(i), 1);
-      mbar_init(epidone(i), 8);  // one arrive per epilogue warp
+      mbar_init(epidone(i), 16);  // one arrive per epilogue warp of BOTH CTAs (only the leader's copy is used)
     }
     mbar_init(hfull, 1);
     mbar_init(hempty, 1);
     if (p.halo) prefetch_tensormap(&p.tmHalo);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
   if (warp == 2 && lane < n_chain) {
     const ChainStage& st = p.st[lane];
     StageLite* l = const_cast<StageLite*>(&lite(lane));
@@ -250,7 +270,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA completion
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -277,11 +298,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     if (lane == 0) {
       const int kb0 = p.st[0].kblocks;
       uint32_t u = 0, ph = 0;
+      // `bytes` = what ONE CTA loads into the slot; the leader's barrier counts the bytes of both
       auto acquire = [&](uint32_t bytes) -> uint32_t {
-        mbar_wait(mempty(u), ph ^ 1u);
-        mbar_arrive_expect_tx(mfull(u), bytes);
+        mbar_wait_cluster(mempty(u), ph ^ 1u);
+        if (leader) mbar_arrive_expect_tx(mfull(u), 2u * bytes);
         return m_base + u * slot_bytes;
       };
+      const int brow = (int)rank * 64;  // this CTA's 64 rows of every 128-row weight block
       auto advance = [&]() {
         if (++u == (uint32_t)p.n_m) {
           u = 0;
@@ -292,16 +315,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       auto load_head = [&](int tile) {
         int x0, y0, n0;
         decode_tile(tile, x0, y0, n0);
-        if (p.halo) {  // the halo once, then one 32 KB slot of weights per tap (both 64-channel halves)
-          mbar_wait(hempty, (heads & 1u) ^ 1u);
-          mbar_arrive_expect_tx(hfull, 2u * kHaloBytes);
-          tma_load_4d(halo_base, &p.tmHalo, hfull, 0, x0 - 1, y0 - 1, n0);
-          tma_load_4d(halo_base + kHaloBytes, &p.tmHalo, hfull, 64, x0 - 1, y0 - 1, n0);
+        if (p.halo) {  // the halo once, then one slot of weights per tap (both 64-channel K blocks, 64 rows each)
+          mbar_wait_cluster(hempty, (heads & 1u) ^ 1u);
+          if (leader) mbar_arrive_expect_tx(hfull, 4u * kHaloBytes);
+          tma_load_4d_pair(halo_base, &p.tmHalo, hfull_l, 0, x0 - 1, y0 - 1, n0);
+          tma_load_4d_pair(halo_base + kHaloBytes, &p.tmHalo, hfull_l, 64, x0 - 1, y0 - 1, n0);
           ++heads;
           for (int tap9 = 0; tap9 < 9; ++tap9) {
-            const uint32_t dst = acquire(2 * kUnitBytes);
-            tma_load_2d(dst, &p.st[0].tmB, mfull(u), (2 * tap9) * 64, 0);
-            tma_load_2d(dst + kUnitBytes, &p.st[0].tmB, mfull(u), (2 * tap9 + 1) * 64, 0);
+            const uint32_t dst = acquire(2 * kSubBytes);
+            tma_load_2d_pair(dst, &p.st[0].tmB, mfull_l(u), (2 * tap9) * 64, brow);
+            tma_load_2d_pair(dst + kSubBytes, &p.st[0].tmB, mfull_l(u), (2 * tap9 + 1) * 64, brow);
             advance();
           }
           return;
@@ -313,9 +336,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             dy = tap / 3 - 1;
             dx = tap - (tap / 3) * 3 - 1;
           }
-          const uint32_t dst = acquire((uint32_t)(1 + nh0) * kUnitBytes);
-          tma_load_4d(dst, &p.tmA, mfull(u), kc * 64, x0 + dx, y0 + dy, n0);
-          for (int h = 0; h < nh0; ++h) tma_load_2d(dst + (1 + h) * kUnitBytes, &p.st[0].tmB, mfull(u), kb * 64, h * 128);
+          const uint32_t dst = acquire((uint32_t)(kUnitBytes + nh0 * kSubBytes));
+          tma_load_4d_pair(dst, &p.tmA, mfull_l(u), kc * 64, x0 + dx, y0 + dy, n0);
+          for (int h = 0; h < nh0; ++h)
+            tma_load_2d_pair(dst + kUnitBytes + h * kSubBytes, &p.st[0].tmB, mfull_l(u), kb * 64, h * 128 + brow);
           advance();
           if (++kc == p.kc_per_tap) {
             kc = 0;
@@ -323,18 +347,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
         }
       };
-      // one 32 KB slot = both 128-row halves of one K block (256 outputs) or two K blocks (128 outputs)
+      // one slot = this CTA's 64 rows of both 128-row halves of one K block (256 outputs) or of two K blocks (128)
       auto load_weights = [&](int i) {
         const int kbn = lite(i).kblocks, nh = lite(i).n >> 7;
         const int slots = (kbn * nh) >> 1;
         for (int sl = 0; sl < slots; ++sl) {
-          const uint32_t dst = acquire(2 * kUnitBytes);
+          const uint32_t dst = acquire(2 * kSubBytes);
           if (nh == 2) {
-            tma_load_2d(dst, &p.st[i].tmB, mfull(u), sl * 64, 0);
-            tma_load_2d(dst + kUnitBytes, &p.st[i].tmB, mfull(u), sl * 64, 128);
+            tma_load_2d_pair(dst, &p.st[i].tmB, mfull_l(u), sl * 64, brow);
+            tma_load_2d_pair(dst + kSubBytes, &p.st[i].tmB, mfull_l(u), sl * 64, 128 + brow);
           } else {
-            tma_load_2d(dst, &p.st[i].tmB, mfull(u), (2 * sl) * 64, 0);
-            tma_load_2d(dst + kUnitBytes, &p.st[i].tmB, mfull(u), (2 * sl + 1) * 64, 0);
+            tma_load_2d_pair(dst, &p.st[i].tmB, mfull_l(u), (2 * sl) * 64, brow);
+            tma_load_2d_pair(dst + kSubBytes, &p.st[i].tmB, mfull_l(u), (2 * sl + 1) * 64, brow);
           }
           advance();
         }
@@ -342,13 +366,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       // issue order (same walk in the MMA warp and in the epilogue warps): a virtual tile -1 runs only the
       // head of tile 0; step s of tile t is stage s+1 (s < head_after), the head of tile t+1
       // (s == head_after) or stage s (s > head_after)
-      const int stride = (int)gridDim.x;
-      for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
-        const bool has_next = tile + stride < total_tiles;
+      for (int t = -1, pt = pt0 - pstride;; ++t, pt += pstride) {
+        const bool has_next = pt + pstride < n_pt;
         for (int sidx = 0; sidx < n_chain; ++sidx) {
           const bool head_step = (n_chain == 1) || (sidx == head_after);
           if (head_step) {
-            if (has_next) load_head(tile + stride);
+            if (has_next) load_head(2 * (pt + pstride) + (int)rank);
           } else if (t >= 0) {
             load_weights(sidx < head_after ? sidx + 1 : sidx);
           }
@@ -360,9 +383,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // ------------------------------------------------------------------ residual slab producer
     if (lane == 0 && p.n_slabs > 0) {
       uint32_t u = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int pt = pt0; pt < n_pt; pt += pstride) {
         int x0, y0, n0;
-        decode_tile(tile, x0, y0, n0);
+        decode_tile(2 * pt + (int)rank, x0, y0, n0);
         for (int i = 0; i < n_chain; ++i) {
           const ChainStage& st = p.st[i];
           if (!st.has_res) continue;
@@ -381,11 +404,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (of the pair)
     // The whole warp runs the loops (warp-uniform control flow and operands: descriptors live in
     // uniform registers, no per-lane waterfall around each tcgen05 instruction); one elected lane issues.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc = umma_idesc_bf16(256, 128);  // 128 rows in each CTA
     const uint64_t desc_hi = umma_smem_desc_sw128(0);  // everything but the 14-bit start address
     const uint32_t n_m = (uint32_t)p.n_m;
     const int kb0 = p.st[0].kblocks;
@@ -400,7 +423,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // overlaps the tensor work instead of sitting between two groups of MMAs.
     bool ring_ready = false;  // outcome of the early probe of slot `mu`
     auto ring_wait = [&]() {
-      if (!ring_ready) mbar_wait(mfull(mu), mph);
+      if (!ring_ready) mbar_wait_cluster(mfull(mu), mph);
       tc_fence_after();
     };
     auto ring_probe_next = [&]() {
@@ -409,7 +432,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         nu = 0;
         nph ^= 1u;
       }
-      ring_ready = mbar_try_wait(mfull(nu), nph);
+      ring_ready = mbar_try_wait_cluster(mfull(nu), nph);
     };
     auto ring_advance = [&]() {
       if (++mu == n_m) {
@@ -423,13 +446,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     uint32_t heads = 0;
     auto issue_head = [&](int t) {
       if (dbg && di < 4000) dbg[di++] = clock64();  // [head start]
-      if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
+      if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait_cluster(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
       if (p.halo) {
         // A operand of tap (dy, dx) = the halo rows shifted by dy*10 + dx: pixel (r, c) of the 8-wide tile is
         // halo row (r+dy)*10 + (c+dx), i.e. 8-row groups 1280 B apart starting at a row offset.  The 128B
         // swizzle is a function of the absolute shared-memory address (what TMA wrote), so the shifted
         // start needs no descriptor base_offset (measured: bit-identical to nine separate TMA boxes).
-        mbar_wait(hfull, heads & 1u);
+        mbar_wait_cluster(hfull, heads & 1u);
         ++heads;
         tc_fence_after();
 #pragma unroll 1
@@ -441,20 +464,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           const uint64_t a1 = desc_halo | (uint64_t)(((a_addr + kHaloBytes) >> 4) & 0x3FFFu);
           const uint32_t b_addr = m_base + mu * slot_bytes;
           const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-          const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kUnitBytes) >> 4) & 0x3FFFu);
+          const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kSubBytes) >> 4) & 0x3FFFu);
           ring_probe_next();
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d0, a0 + 2u * k, b0 + 2u * k, idesc, (tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(d0, a0 + 2u * k, b0 + 2u * k, idesc, (tap | k) != 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d0, a1 + 2u * k, b1 + 2u * k, idesc, 1u);
-            umma_commit(mempty(mu));
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(d0, a1 + 2u * k, b1 + 2u * k, idesc, 1u);
+            umma_commit_pair(mempty(mu));
           }
           ring_advance();
         }
         if (elect_one()) {
-          umma_commit(hempty);  // the halo may be overwritten once these MMAs retire
-          umma_commit(accfull(0));
+          umma_commit_pair(hempty);  // the halo may be overwritten once these MMAs retire
+          umma_commit_pair(accfull(0));
         }
         if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
         return;
@@ -465,21 +488,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         const uint32_t a_addr = m_base + mu * slot_bytes;
         const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
         const uint64_t b0 = desc_hi | (uint64_t)(((a_addr + kUnitBytes) >> 4) & 0x3FFFu);
-        const uint64_t b1 = desc_hi | (uint64_t)(((a_addr + 2 * kUnitBytes) >> 4) & 0x3FFFu);
+        const uint64_t b1 = desc_hi | (uint64_t)(((a_addr + kUnitBytes + kSubBytes) >> 4) & 0x3FFFu);
         ring_probe_next();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 bytes inside the 128B swizzle atom
-            umma_bf16(d0, adesc + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_pair(d0, adesc + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           if (nh0 == 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d1, adesc + 2u * k, b1 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(d1, adesc + 2u * k, b1 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(mempty(mu));  // frees the ring stage once these MMAs retire
+          umma_commit_pair(mempty(mu));  // frees the ring stage (in both CTAs) once these MMAs retire
         }
         ring_advance();
       }
-      if (elect_one()) umma_commit(accfull(0));
+      if (elect_one()) umma_commit_pair(accfull(0));
       if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
     };
 
@@ -492,8 +515,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const uint32_t c0 = tmem_base + (uint32_t)L.col0, c1 = tmem_base + (uint32_t)L.col1;
       const uint32_t x0c = tmem_base + (uint32_t)Lp.col0, x1c = tmem_base + (uint32_t)Lp.col1;
       const int hz = L.hz, hzd = L.hzd;
-      mbar_wait(epidone(i - 1), par);  // operand of this stage is complete in tensor memory
-      if (hz >= 0 && t - hzd >= 0) mbar_wait(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
+      mbar_wait_cluster(epidone(i - 1), par);  // operand of this stage is complete in tensor memory (both CTAs)
+      if (hz >= 0 && t - hzd >= 0) mbar_wait_cluster(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
       tc_fence_after();
       if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
       const int slots = (kbn * nh) >> 1;
@@ -502,37 +525,36 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         ring_wait();
         const uint32_t b_addr = m_base + mu * slot_bytes;
         const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-        const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kUnitBytes) >> 4) & 0x3FFFu);
+        const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kSubBytes) >> 4) & 0x3FFFu);
         ring_probe_next();
         if (elect_one()) {
           if (nh == 2) {  // K block sl, both output halves
             const uint32_t xa = ((sl >> 1) ? x1c : x0c) + (sl & 1) * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(c1, xa + k * 8, b1 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c1, xa + k * 8, b1 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
           } else {        // K blocks 2 sl and 2 sl + 1 of a 128-wide stage
             const uint32_t xa = sl ? x1c : x0c;  // K blocks 0,1 live in the first operand half, 2,3 in the second
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(c0, xa + 64 + k * 8, b1 + 2u * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c0, xa + 64 + k * 8, b1 + 2u * k, idesc, 1u);
           }
-          umma_commit(mempty(mu));
+          umma_commit_pair(mempty(mu));
         }
         ring_advance();
       }
-      if (elect_one()) umma_commit(accfull(i));  // accumulator ready; the consumed operand may be overwritten
+      if (elect_one()) umma_commit_pair(accfull(i));  // accumulator ready; the consumed operand may be overwritten
       if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
       if (p.dbg_exec) {  // probe only: how long until the accumulator is complete (serialises this warp)
-        mbar_wait(accfull(i), par);
+        mbar_wait_cluster(accfull(i), par);
         if (dbg && di < 4000) dbg[di++] = clock64();
       }
     };
 
-    const int stride = (int)gridDim.x;
-    for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
-      const bool has_next = tile + stride < total_tiles;
+    for (int t = -1, pt = pt0 - pstride;; ++t, pt += pstride) {
+      const bool has_next = pt + pstride < n_pt;
 #pragma unroll 1
       for (int sidx = 0; sidx < n_chain; ++sidx) {
         const bool head_step = (n_chain == 1) || (sidx == head_after);
@@ -581,7 +603,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const float4* const sc2 = sh1 + (st.n >> 2);
       const float4* const sh2 = sc2 + (st.n >> 2);
       if (dbg && di < dend) dbg[di++] = clock64();  // [stage i entered]
-      mbar_wait_warp(accfull(i), (uint32_t)t & 1u);
+      if (lane == 0) mbar_wait_cluster(accfull(i), (uint32_t)t & 1u);  // one polling lane (see mbar_wait_warp)
+      __syncwarp();
       tc_fence_after();
       if (dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
       const uint32_t t_lo = tmem_base + lane_base + (uint32_t)st.col0, t_hi = tmem_base + lane_base + (uint32_t)st.col1;
@@ -629,16 +652,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       if (x_src) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(epidone(i));
+      if (lane == 0) mbar_arrive_cluster(epidone_l(i));  // counted on the leader's barrier
       if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
     };
 
-    const int stride = (int)gridDim.x;
     int x0 = 0, y0 = 0, n0 = 0;
-    for (int t = -1, tile = (int)blockIdx.x - stride;; ++t, tile += stride) {
-      const bool has_next = tile + stride < total_tiles;
+    for (int t = -1, pt = pt0 - pstride;; ++t, pt += pstride) {
+      const bool has_next = pt + pstride < n_pt;
       int nx0 = 0, ny0 = 0, nn0 = 0;
-      if (has_next) decode_tile(tile + stride, nx0, ny0, nn0);
+      if (has_next) decode_tile(2 * (pt + pstride) + (int)rank, nx0, ny0, nn0);
 #pragma unroll 1
       for (int sidx = 0; sidx < n_chain; ++sidx) {
         const bool head_step = (n_chain == 1) || (sidx == head_after);
@@ -653,9 +675,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   }
 
+  // neither CTA may leave (or free its tensor memory) while the other can still signal its barriers
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -780,13 +804,14 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
   // shared-memory budget: constants, barriers, residual slabs, the rest is the operand ring
   p.aff_bytes = (aff_floats * 4 + 255) & ~255;
   p.slab_bytes = kUnitBytes + (any_res2 ? kUnitBytes / 4 : 0);
-  p.slot_bytes = (1 + (p.st[0].n >> 7)) * kUnitBytes;
-  if (p.slot_bytes < 2 * kUnitBytes) p.slot_bytes = 2 * kUnitBytes;
+  // ring slot (per CTA): two 64-row weight sub-tiles; without the halo a head K block = A tile + its sub-tiles
+  p.slot_bytes = 2 * kSubBytes;
+  if (!p.halo) p.slot_bytes = kUnitBytes + (p.st[0].n >> 7) * kSubBytes;
   if (p.halo) {
     DF3D_REQUIRE(p.taps == 9 && p.kc_per_tap == 2 && p.st[0].n == 128 && p.tw == 8 && p.th == 16 && p.nb == 1, DF3D_EINVAL,
                  "launch_conv_chain: halo mode needs a 3x3 head with 128 input and output channels on 8 x 16 tiles");
   }
-  p.n_slabs = any_slab ? (p.halo ? 3 : 4) : 0;
+  p.n_slabs = any_slab ? 4 : 0;
   if (const char* env = getenv("DF3D_CHAIN_NS")) {  // profiling knob: residual slab depth
     const int v = atoi(env);
     if (any_slab && v >= 2 && v <= kMaxSlabs) p.n_slabs = v;
@@ -813,8 +838,23 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
   };
   p.tx_shift = log2_exact(p.tiles_x);
   p.ty_shift = log2_exact(p.tiles_y);
-  const int grid = total < num_sms ? total : num_sms;
-  conv_chain_kernel<<<grid, kChainThreads, smem, stream>>>(p);
+  // clusters of two CTAs (one TPC): an even grid, one pair per two tiles
+  const int pairs = (total + 1) / 2;
+  const int grid = 2 * (pairs < num_sms / 2 ? pairs : num_sms / 2);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DF3D_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, p));
   DF3D_LAUNCH_CHECK("conv_chain_kernel");
   return DF3D_OK;
 }

@@ -19,7 +19,7 @@ namespace df3d {
 constexpr int kMaxChain = 5;
 
 struct ChainStage {
-  CUtensorMap tmB;     // weights, 2-D (K, N) K-major, box (64, 128), SWIZZLE_128B
+  CUtensorMap tmB;     // weights, 2-D (K, N) K-major, box (64, 64) = one CTA's half of a 128-row block, SWIZZLE_128B
   CUtensorMap tmRes;   // residual added in this stage's epilogue: 4-D box (64, tw, th, nb)
   CUtensorMap tmRes2;  // second residual at half resolution (nearest x2 up-sample + add)
   // epilogue:  v = acc*scale1[c] + shift1[c] (+ residual) (+ up(residual2)) ; relu1 ;
@@ -57,7 +57,7 @@ struct ChainParams {
   // shared-memory carve-up (filled by launch_conv_chain)
   int head_after;  // the head GEMM of the next tile is issued behind this stage (filled by launch_conv_chain)
   int n_m;         // operand ring slots
-  int slot_bytes;  // 32 KB (48 KB for a 256-wide head): a head K block (A + weight half-tiles) or 32 KB of weights
+  int slot_bytes;  // per CTA: 16 KB of weights (two 64-row sub-tiles), or a head K block (A tile + its sub-tiles)
   int tx_shift, ty_shift;  // log2 of tiles_x / tiles_y when they are powers of two, else -1
   int n_slabs;     // residual slabs (TMA prefetch ring)
   int slab_bytes;  // 16384 (+4096 with a half-resolution residual)

@@ -538,7 +538,7 @@ struct Emitter {
     for (int i = 0; i < n; ++i) {
       const StageSpec& s = sp[i];
       ChainStage& st = p.st[i];
-      if ((err = make_tmap_wgt(&st.tmB, hg->d_w + s.w_off, s.K, s.N, 128))) return;
+      if ((err = make_tmap_wgt(&st.tmB, hg->d_w + s.w_off, s.K, s.N, 64))) return;  // 64 rows: one CTA's half of an N = 128 block
       st.n = s.N;
       st.kblocks = s.K / 64;
       st.relu1 = s.relu1 ? 1 : 0;

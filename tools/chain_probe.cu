@@ -75,7 +75,7 @@ int main(int argc, char** argv) {
   int n = 0;
   auto stage = [&](int K, int N, size_t woff) -> ChainStage& {
     ChainStage& st = p.st[n++];
-    rc |= make_tmap_wgt(&st.tmB, wts + woff, K, N, 128);
+    rc |= make_tmap_wgt(&st.tmB, wts + woff, K, N, 64);
     st.n = N;
     st.kblocks = K / 64;
     st.scale1 = aff;
