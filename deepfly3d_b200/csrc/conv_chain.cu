@@ -13,7 +13,9 @@
 //   warp 1  leader CTA (rank 0): MMA issuer; both CTAs: TMEM owner (warp-uniform loop, one elected lane issues)
 //   warp 2  TMA producer of the residual slabs (64 channels x 128 pixels, + the half-resolution slab
 //           of the up-sample branch), a ring that prefetches across stages and tiles
-//   warp 3  idle
+//   warp 3  idle.  Warps 0..3 (warpgroup 0) give registers back (setmaxnreg 56) so that the epilogue
+//           warpgroups can take 224 each: the heavy epilogues spilled at the 168 registers a 384-thread
+//           block allows, and with 227 KB of shared memory (no L1) a spill reload is an L2 round trip
 //   warps 4..11  epilogue: two groups of four warps (one TMEM lane quarter each), group g takes the
 //           64-channel slabs sl = g, g+2 of every stage
 //
@@ -275,7 +277,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
   auto decode_tile = [&](int tile, int& x0, int& y0, int& n0) {
     int tx, ty, tb;
     if (p.tx_shift >= 0 && p.ty_shift >= 0) {
@@ -293,6 +294,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     n0 = tb * p.nb;
   };
 
+  // register re-allocation between the warpgroups, inside the role branches so that ptxas budgets each role
+  // separately (per scheduler: 120 + 2 x 192 = 504 of 512 registers per lane)
+  if (warp < kEpiWarp0c) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
   if (warp == 0) {
     // ------------------------------------------------------------------ ring producer (issue order of the MMA warp)
     if (lane == 0) {
@@ -568,6 +572,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   } else if (warp >= kEpiWarp0c) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int grp = (warp - kEpiWarp0c) >> 2; // slab parity this group handles
     const int m = q * 32 + lane;              // row of the tile = pixel
