@@ -87,83 +87,115 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
 
+// Two fp32 lanes per instruction (FADD2 / FFMA2): same IEEE results as the scalar forms, half the issue slots.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 bf2_unpack(uint32_t x) { return make_float2(bf_lo(x), bf_hi(x)); }
+
+// Operands of one group of 8 channels of a slab, fetched from shared memory two groups ahead of their use
+// (unused members are dead code in the specialisations that do not need them).
+struct EpiGroup {
+  float4 sc1[2], sh1[2], sc2[2], sh2[2];
+  uint4 res, up;
+};
+
 // Epilogue of one 64-channel slab of one stage for one pixel row (one thread), fully specialised:
 //   UNIT  scale1 == 1 (conv without a folded BatchNorm): v = acc + shift1
 //   RES   + residual (bf16, swizzled slab row)     RES2  + nearest-x2 up-sampled half-resolution residual
 //   RELU  relu after the adds                      XSRC  0: no operand, 1: bf16(v), 2: relu(bn2(bf16(v)))
 //   OUT   bf16(v) to global memory
 // t_slab: TMEM address of the slab's 64 fp32 accumulator columns (the operand is written back in place
-// over the first 32); c1/c2: this slab's first channel in the constant arrays.  One 32-column half at a
-// time keeps the live registers low: with 227 KB of shared memory there is no L1 left, so a spilled
-// register is an L2 round trip.
+// over the first 32); c1/c2: this slab's first channel in the constant arrays.
+// Software pipeline (measured: the straight version issued 1 instruction in 4 cycles, half of the stalls on
+// shared-memory loads, a quarter behind tcgen05.ld): the slab is four quarters of 16 columns; the
+// tcgen05.ld of quarter q+1 is in flight while quarter q is processed, and the constants / residual rows of
+// group j+2 are loaded before group j is computed.
 template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT>
 __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restrict__ sc1,
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
                                          const float4* __restrict__ sh2, const uint8_t* __restrict__ rrow,
                                          const uint8_t* __restrict__ rrow2, uint32_t sw, uint32_t sw2, uint32_t x_addr,
                                          uint8_t* out, bool store) {
+  auto fetch = [&](EpiGroup& g, int j) {  // j: group of 8 channels, 0..7
+    g.sh1[0] = sh1[2 * j];
+    g.sh1[1] = sh1[2 * j + 1];
+    if (!UNIT) {
+      g.sc1[0] = sc1[2 * j];
+      g.sc1[1] = sc1[2 * j + 1];
+    }
+    if (RES) g.res = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)j ^ sw) << 4));
+    if (RES2) g.up = *reinterpret_cast<const uint4*>(rrow2 + (((uint32_t)j ^ sw2) << 4));
+    if (XSRC == 2) {
+      g.sc2[0] = sc2[2 * j];
+      g.sc2[1] = sc2[2 * j + 1];
+      g.sh2[0] = sh2[2 * j];
+      g.sh2[1] = sh2[2 * j + 1];
+    }
+  };
+  EpiGroup g[3];
+  uint32_t acc[2][16];
+  tmem_ld_32x16(t_slab, acc[0]);
+  fetch(g[0], 0);
+  fetch(g[1], 1);
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t r[32];
-    tmem_ld_32x32(t_slab + half * 32, r);
+  for (int q = 0; q < 4; ++q) {
     tmem_ld_wait();
-    uint32_t xp[16], op[16];
+    if (q + 1 < 4) tmem_ld_32x16(t_slab + (q + 1) * 16, acc[(q + 1) & 1]);
+    uint32_t op[8], xp[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {  // 8 channels = one 16-byte chunk of the swizzled slab row
-      const int c4 = (half * 32 + j * 8) >> 2;
-      float v[8];
-      {
-        const float4 ha = sh1[c4], hb = sh1[c4 + 1];
-        const float t1[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-        if (UNIT) {
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * q + h;
+      if (j + 2 < 8) fetch(g[(j + 2) % 3], j + 2);
+      const EpiGroup& G = g[j % 3];
+      const uint32_t* a = acc[q & 1] + 8 * h;
+      const float2 t1[4] = {make_float2(G.sh1[0].x, G.sh1[0].y), make_float2(G.sh1[0].z, G.sh1[0].w),
+                            make_float2(G.sh1[1].x, G.sh1[1].y), make_float2(G.sh1[1].z, G.sh1[1].w)};
+      const float2 s1[4] = {make_float2(G.sc1[0].x, G.sc1[0].y), make_float2(G.sc1[0].z, G.sc1[0].w),
+                            make_float2(G.sc1[1].x, G.sc1[1].y), make_float2(G.sc1[1].z, G.sc1[1].w)};
+      const uint32_t rw[4] = {G.res.x, G.res.y, G.res.z, G.res.w};
+      const uint32_t uw[4] = {G.up.x, G.up.y, G.up.z, G.up.w};
+      float2 v[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]) + t1[e];
-        } else {
-          const float4 sa = sc1[c4], sb = sc1[c4 + 1];
-          const float s1[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[j * 8 + e]), s1[e], t1[e]);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float2 ac = make_float2(__uint_as_float(a[2 * e]), __uint_as_float(a[2 * e + 1]));
+        v[e] = UNIT ? fadd2(ac, t1[e]) : ffma2(ac, s1[e], t1[e]);
+        if (RES) v[e] = fadd2(v[e], bf2_unpack(rw[e]));
+        if (RES2)  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
+          v[e] = fadd2(bf2_unpack(pack2(v[e].x, v[e].y)), bf2_unpack(uw[e]));
+        op[4 * h + e] = RELU ? pack2_relu(v[e].x, v[e].y) : pack2(v[e].x, v[e].y);
       }
-      if (RES) {
-        const uint4 rr = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(half * 4 + j) ^ sw) << 4));
-        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[2 * e] += bf_lo(rw[e]);
-          v[2 * e + 1] += bf_hi(rw[e]);
-        }
-      }
-      if (RES2) {  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
-        const uint4 rr = *reinterpret_cast<const uint4*>(rrow2 + (((uint32_t)(half * 4 + j) ^ sw2) << 4));
-        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t pk = pack2(v[2 * e], v[2 * e + 1]);
-          v[2 * e] = bf_lo(pk) + bf_lo(rw[e]);
-          v[2 * e + 1] = bf_hi(pk) + bf_hi(rw[e]);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) op[j * 4 + e] = RELU ? pack2_relu(v[2 * e], v[2 * e + 1]) : pack2(v[2 * e], v[2 * e + 1]);
       if (XSRC == 2) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
-        const float4 sa = sc2[c4], sb = sc2[c4 + 1], ha = sh2[c4], hb = sh2[c4 + 1];
-        const float s2[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-        const float t2[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const float2 s2[4] = {make_float2(G.sc2[0].x, G.sc2[0].y), make_float2(G.sc2[0].z, G.sc2[0].w),
+                              make_float2(G.sc2[1].x, G.sc2[1].y), make_float2(G.sc2[1].z, G.sc2[1].w)};
+        const float2 t2[4] = {make_float2(G.sh2[0].x, G.sh2[0].y), make_float2(G.sh2[0].z, G.sh2[0].w),
+                              make_float2(G.sh2[1].x, G.sh2[1].y), make_float2(G.sh2[1].z, G.sh2[1].w)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t ow = op[j * 4 + e];
-          xp[j * 4 + e] = pack2_relu(fmaf(bf_lo(ow), s2[2 * e], t2[2 * e]), fmaf(bf_hi(ow), s2[2 * e + 1], t2[2 * e + 1]));
+          const float2 x = ffma2(bf2_unpack(op[4 * h + e]), s2[e], t2[e]);
+          xp[4 * h + e] = pack2_relu(x.x, x.y);
         }
       }
     }
-    if (XSRC == 1) tmem_st_32x16(x_addr + half * 16, op);
-    if (XSRC == 2) tmem_st_32x16(x_addr + half * 16, xp);
+    if (XSRC == 1) tmem_st_32x8(x_addr + q * 8, op);
+    if (XSRC == 2) tmem_st_32x8(x_addr + q * 8, xp);
     if (OUT) {
-      if (store) {  // 32 channels = 64 contiguous bytes of this thread's pixel: two full 32-byte sectors
-        stg256(out + half * 64, op);
-        stg256(out + half * 64 + 32, op + 8);
-      }
+      // 16 channels = 32 contiguous bytes of this thread's pixel: one full sector.  (Staging the slab in shared
+      // memory for one TMA store was measured too: the stores leave the warps' issue path, but the 32 KB of
+      // staging cost two slots of the weight ring or a residual slab, and either loss outweighs the gain.)
+      if (store) stg256(out + q * 32, op);
     }
   }
 }
@@ -551,7 +583,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       }
       if (elect_one()) umma_commit_pair(accfull(i));  // accumulator ready; the consumed operand may be overwritten
       if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
-      if (p.dbg_exec) {  // probe only: how long until the accumulator is complete (serialises this warp)
+      if (p.dbg_exec & 1) {  // probe only: how long until the accumulator is complete (serialises this warp)
         mbar_wait_cluster(accfull(i), par);
         if (dbg && di < 4000) dbg[di++] = clock64();
       }
@@ -597,7 +629,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // epilogue of stage i of the tile (local number t) at pixel offsets x0, y0, n0
     auto run_stage = [&](int i, int t, int x0, int y0, int n0) {
       const StageLite& st = lite(i);
-      const bool in_batch = (n0 + pn) < p.B;  // partially filled multi-image tiles: skip the stores
+      const bool in_batch = (n0 + pn) < p.B && !(p.dbg_exec & 2);  // partially filled multi-image tiles: skip the stores
       const size_t pixel = ((size_t)(n0 + pn) * p.H + (y0 + phh)) * p.W + (x0 + pw);
       const bool has_res = st.has_res != 0;
       const int x_src = st.x_src, kind = st.kind;

@@ -26,6 +26,7 @@ int main(int argc, char** argv) {
   const int taps = argc > 1 ? atoi(argv[1]) : 9;
   const int B = argc > 2 ? atoi(argv[2]) : 224;
   const int variant = argc > 3 ? atoi(argv[3]) : 0;
+  const int nores = argc > 6 ? atoi(argv[6]) : 0;  // 1: no residual slabs at all (timing experiment)
   const int H = 64, W = 64;
   if (tma_init() || conv_chain_configure()) {
     printf("init failed: %s\n", df3d_last_error());
@@ -96,7 +97,7 @@ int main(int argc, char** argv) {
     s1.unit_scale = 1;
     s1.has_res = 1;
     rc |= make_tmap_act(&s1.tmRes, res, 256, W, H, B, tw, th, nb);
-    if (variant == 0) {
+    if (variant == 0 && nores < 2) {
       s1.has_res2 = 1;
       rc |= make_tmap_box(&s1.tmRes2, half, 256, W / 2, H / 2, B, tw / 2, th / 2, nb);
     }
@@ -151,7 +152,7 @@ int main(int argc, char** argv) {
   // MMA warp stamps: head(0) start/issued, then per tile: for each stage i >= 1 (ready, issued), with the next
   // head's (start, issued) behind stage head_after.  Epilogue stamps: (ready, done) per stage in its own order.
   const int per = 2 * n;  // stamps per tile in steady state, both roles
-  const int per_m = per + (p.dbg_exec ? n - 1 : 0);
+  const int per_m = per + ((p.dbg_exec & 1) ? n - 1 : 0);
   printf("MMA warp, tiles 20..23: deltas in clock cycles between consecutive stamps (period = %d stamps per tile)\n", per);
   for (int t = 20; t < 24; ++t) {
     printf("  tile %d:", t);
