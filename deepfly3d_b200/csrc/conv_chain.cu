@@ -38,6 +38,7 @@
 #include <initializer_list>
 
 #include "conv_chain.cuh"
+#include "conv_gemm.cuh"  // tensor-map helpers
 #include "sm100.cuh"
 
 namespace df3d {
@@ -128,7 +129,7 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
                                          const float4* __restrict__ sh2, const uint8_t* __restrict__ rrow,
                                          const uint8_t* __restrict__ rrow2, uint32_t sw, uint32_t sw2, uint32_t x_addr,
-                                         uint8_t* out, bool store) {
+                                         uint8_t* out, bool store, uint32_t rrow_s) {
   auto fetch = [&](EpiGroup& g, int j) {  // j: group of 8 channels, 0..7
     g.sh1[0] = sh1[2 * j];
     g.sh1[1] = sh1[2 * j + 1];
@@ -191,7 +192,14 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
     }
     if (XSRC == 1) tmem_st_32x8(x_addr + q * 8, op);
     if (XSRC == 2) tmem_st_32x8(x_addr + q * 8, xp);
-    if (OUT) {
+    if (OUT && RES) {
+      // Stored stage with a residual: bf16(v) replaces the residual it was computed from, in place in the
+      // slab (this thread read those two chunks two groups ago); the warp's 32 rows then leave with one TMA
+      // store (run_stage).  256-bit stores from registers, one pixel row per lane, cost the LSU data pipe
+      // ~50 wavefronts per instruction (measured: 4 900 of the 9 500 LSU wavefronts of a tile).
+      sts128(rrow_s + (((uint32_t)(2 * q) ^ sw) << 4), make_uint4(op[0], op[1], op[2], op[3]));
+      sts128(rrow_s + (((uint32_t)(2 * q + 1) ^ sw) << 4), make_uint4(op[4], op[5], op[6], op[7]));
+    } else if (OUT) {
       // 16 channels = 32 contiguous bytes of this thread's pixel: one full sector.  (Staging the slab in shared
       // memory for one TMA store was measured too: the stores leave the warps' issue path, but the 32 KB of
       // staging cost two slots of the weight ring or a residual slab, and either loss outweighs the gain.)
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       prefetch_tensormap(&p.st[i].tmB);
       if (p.st[i].has_res) prefetch_tensormap(&p.st[i].tmRes);
       if (p.st[i].has_res2) prefetch_tensormap(&p.st[i].tmRes2);
+      if (p.st[i].has_res && p.st[i].out_raw) prefetch_tensormap(&p.st[i].tmOutQ);
     }
     for (int s = 0; s < p.n_m; ++s) {
       mbar_init(mfull(s), 1);
@@ -620,6 +629,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       row2_off = (uint32_t)r2 * 128u;
       sw2 = (uint32_t)(r2 & 7);
     }
+    // this warp's quarter of the tile (32 consecutive pixels) as a TMA sub-box: offsets inside the tile
+    const int rpq = 32 / p.tw;  // rows per quarter
+    const int qx = 0, qy = (q * rpq) % p.th, qn = (q * rpq) / p.th;
+    constexpr uint32_t kNoSlab = 0xffffffffu;
+    uint32_t pending = kNoSlab;     // lane 0: slab whose TMA store may still be reading it
     uint32_t spos = 0, sphase = 0;  // ring position / phase of the next residual slab (slab 0 of the next stage with one)
     const uint32_t n_slabs = (uint32_t)p.n_slabs;
     unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
@@ -659,22 +673,37 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           mbar_wait_warp(sfull(su), sph);
           slab = s_base + su * (uint32_t)p.slab_bytes;
         }
+        const uint32_t rrow_s = slab + row_off;
         const uint8_t* const rrow = sm + (slab - smem_base) + row_off;
         const uint8_t* const rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off;
         const float4 *c1 = sc1 + sl * 16, *h1 = sh1 + sl * 16, *c2 = sc2 + sl * 16, *h2 = sh2 + sl * 16;
         uint8_t* const o = out_row + sl * 128;
         // the operand of the next stage replaces the first 32 of the 64 columns just read (in place)
         switch (kind) {  //          UNIT   RES    RES2   RELU  XSRC OUT
-          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
-          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch); break;
+          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
           default: break;  // launch_conv_chain rejects anything else
         }
-        if (has_res) {  // slab consumed by this warp
+        if (has_res && st.out) {
+          // in-place output: this warp's 32 rows of the slab go out as one TMA store; the slab is handed back
+          // to the producer once the store has read it -- one slab later, so that nobody waits for that
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (!(p.dbg_exec & 2)) tma_store_4d(&p.st[i].tmOutQ, slab + (uint32_t)q * 4096u, sl * 64, x0 + qx, y0 + qy, n0 + qn);
+            tma_store_commit();
+            if (pending != kNoSlab) {
+              tma_store_wait_read<1>();
+              mbar_arrive(sempty(pending));
+            }
+            pending = su;
+          }
+        } else if (has_res) {  // slab consumed by this warp
           __syncwarp();
           if (lane == 0) mbar_arrive(sempty(su));
         }
@@ -690,6 +719,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(epidone_l(i));  // counted on the leader's barrier
+      if (lane == 0 && pending != kNoSlab) {  // after the hand-over to the tensor pipe: release the last stored slab
+        tma_store_wait_read<0>();
+        mbar_arrive(sempty(pending));
+        pending = kNoSlab;
+      }
       if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
     };
 
@@ -710,6 +744,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       y0 = ny0;
       n0 = nn0;
     }
+    if (lane == 0) tma_store_wait_all();  // every output tile has left shared memory and is written
   }
 
   // neither CTA may leave (or free its tensor memory) while the other can still signal its barriers
@@ -720,6 +755,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------ host
+int make_tmap_quarter(CUtensorMap* out, const void* base, int C, int W, int H, int N, int tw, int th, int nb) {
+  DF3D_REQUIRE(tw > 0 && 32 % tw == 0 && tw * th * nb == 128, DF3D_EINVAL, "make_tmap_quarter: bad tile %d x %d x %d", tw, th, nb);
+  const int rows = 32 / tw;
+  if (rows <= th) {
+    DF3D_REQUIRE(th % rows == 0, DF3D_EINVAL, "make_tmap_quarter: bad tile %d x %d x %d", tw, th, nb);
+    return make_tmap_box(out, base, C, W, H, N, tw, rows, 1);
+  }
+  DF3D_REQUIRE(rows % th == 0, DF3D_EINVAL, "make_tmap_quarter: bad tile %d x %d x %d", tw, th, nb);
+  return make_tmap_box(out, base, C, W, H, N, tw, th, rows / th);
+}
+
 int conv_chain_configure() {
   DF3D_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemLimit));
   return DF3D_OK;

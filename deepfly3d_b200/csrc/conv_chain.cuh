@@ -22,6 +22,8 @@ struct ChainStage {
   CUtensorMap tmB;     // weights, 2-D (K, N) K-major, box (64, 64) = one CTA's half of a 128-row block, SWIZZLE_128B
   CUtensorMap tmRes;   // residual added in this stage's epilogue: 4-D box (64, tw, th, nb)
   CUtensorMap tmRes2;  // second residual at half resolution (nearest x2 up-sample + add)
+  CUtensorMap tmOutQ;  // stages with a residual AND out_raw: out_raw as a TMA store target, box = one warp's quarter of
+                       // the tile (64 channels x 32 consecutive pixels, see make_tmap_quarter)
   // epilogue:  v = acc*scale1[c] + shift1[c] (+ residual) (+ up(residual2)) ; relu1 ;
   //            raw = bf16(v) ; act = bf16(relu(raw*scale2[c] + shift2[c]))
   const float* scale1;
@@ -70,5 +72,7 @@ struct ChainParams {
 
 int conv_chain_configure();
 int launch_conv_chain(const ChainParams& p, int num_sms, cudaStream_t stream);
+// TMA box of 32 consecutive pixels of a (tw, th, nb) tile: (64, tw, 32/tw, 1) or (64, tw, th, 32/(tw*th))
+int make_tmap_quarter(CUtensorMap* out, const void* base, int C, int W, int H, int N, int tw, int th, int nb);
 
 }  // namespace df3d

@@ -567,6 +567,7 @@ struct Emitter {
           return;
         }
         st.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*s.out_raw));
+        if (st.has_res && (err = make_tmap_quarter(&st.tmOutQ, ptr(*s.out_raw), s.N, in.W, in.H, B, tw, th, nb))) return;
         bytes_px += 2.0 * s.N;
       }
       op.flops_per_image += s.flop_per_px * in.H * in.W;

@@ -113,10 +113,12 @@ int main(int argc, char** argv) {
       s3.has_res = 1;
       rc |= make_tmap_act(&s3.tmRes, res, 256, W, H, B, tw, th, nb);
       s3.out_raw = y;
+      rc |= make_tmap_quarter(&s3.tmOutQ, y, 256, W, H, B, tw, th, nb);
       s3.x_src = 2;
       names[n - 1] = "merged";
     } else {
       s1.out_raw = y;
+      rc |= make_tmap_quarter(&s1.tmOutQ, y, 256, W, H, B, tw, th, nb);
       s1.x_src = variant == 2 ? 0 : 2;
     }
   }
