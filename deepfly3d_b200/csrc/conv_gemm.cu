@@ -5,11 +5,15 @@
 //     per (tap, channel block); the 3x3 halo / zero padding is the TMA's out-of-bounds zero fill
 //     (coordinates x0+dx-1, y0+dy-1 may be -1 or W/H).
 //   * B tile: BN output channels x 64 K, 2-D TMA from the packed [CoutPad][taps*CinPad] weights.
-//   * one CTA per SM, persistent over tiles, 7 warps:
+//   * one CTA per SM, persistent over tiles, 12 warps:
 //       warp 0  TMA producer of the A/B ring          warp 1  MMA issuer (one thread) + TMEM owner
-//       warp 2  TMA producer of the residual ring     warps 3..6  epilogue (one TMEM lane quarter each)
+//       warp 2  TMA producer of the residual ring     warp 3  idle
+//       warps 4..11  epilogue: two groups of four warps (one TMEM lane quarter each); group g takes the
+//                    tiles of accumulator stage g (every other tile).  With one group the small-K convs
+//                    (1x1, K = 64..256: the 128x128-resolution layers, the pooled conv1s) were bound by the
+//                    epilogue -- 4 200 cycles per 128-pixel tile for an HBM cost of 1 900 (measured).
 //   * TMEM holds two accumulator stages (2 x BN fp32 columns): the epilogue of tile i overlaps the
-//     MMAs of tile i+1.
+//     MMAs of tile i+1 and the epilogue of tile i-1.
 //   * epilogue, per 64-channel slab: tcgen05.ld -> scale/shift (+ residual slab from shared memory,
 //     prefetched by TMA) -> ReLU / bf16 rounding -> 128B-swizzled shared-memory slab -> TMA store.
 //     Every global access of the kernel is a TMA bulk transfer (fully coalesced, asynchronous); the
@@ -23,8 +27,8 @@ namespace df3d {
 
 using namespace sm100;
 
-constexpr int kConvThreads = 224;
-constexpr int kEpiWarp0 = 3;            // first epilogue warp
+constexpr int kConvThreads = 384;
+constexpr int kEpiWarp0 = 4;            // first epilogue warp
 constexpr int kEpiThreads = 128;
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // 128 rows x 64 bf16
@@ -213,11 +217,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 3..6)
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue (warps 4..11)
     const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int grp = (warp - kEpiWarp0) >> 2;  // accumulator stage / tile parity of this group
     const int m = q * 32 + lane;       // row of the tile = pixel
-    const bool leader = (warp == kEpiWarp0) && (lane == 0);
+    const bool leader = (q == 0) && (lane == 0);
+    const uint32_t bar_a = 1u + 2u * (uint32_t)grp, bar_b = 2u + 2u * (uint32_t)grp;
     const uint32_t row_off = (uint32_t)m * 128u;
     const uint32_t sw = (uint32_t)(m & 7);
     // row of this pixel's parent in the half-resolution residual slab (box tw/2 x th/2 x nb)
@@ -228,9 +234,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       row2_off = (uint32_t)r2 * 128u;
       sw2 = (uint32_t)(r2 & 7);
     }
-    uint32_t it = 0, rslot = 0, rphase = 0, obuf = 0;
+    uint32_t it = 0, rslot = 0, rphase = 0;
+    const uint32_t obuf = (uint32_t)grp;  // one staging buffer per group and output kind
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      if (as != (uint32_t)grp) {  // the other group's tile: only keep the residual ring position in step
+        if (has_res && !p.out_f32) {
+          rslot += kSlabs;
+          while (rslot >= (uint32_t)n_res) {
+            rslot -= (uint32_t)n_res;
+            rphase ^= 1u;
+          }
+        }
+        continue;
+      }
       int nt, x0, y0, n0;
       decode_tile(tile, nt, x0, y0, n0);
       mbar_wait_warp(tfull_bar(as), aphase);
@@ -265,6 +282,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t rbuf2 = res_base + rslot * res_slot_bytes + kSlabBytes + row2_off;
           const uint32_t raw_buf = raw_base + obuf * kSlabBytes + row_off;
           const uint32_t act_buf = act_base + obuf * kSlabBytes + row_off;
+          // the group's previous bulk store must have read the staging buffer out (a tile ago for one-slab tiles)
+          if (leader) tma_store_wait_read<0>();
+          named_bar_sync(bar_a, kEpiThreads);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
@@ -343,16 +363,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
           fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA store
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(bar_b, kEpiThreads);
           if (leader) {
             const int c0 = nt * BN + sl * 64;
             if (has_raw) tma_store_4d(&p.tmRaw, raw_base + obuf * kSlabBytes, c0, x0, y0, n0);
             if (has_act) tma_store_4d(&p.tmAct, act_base + obuf * kSlabBytes, c0, x0, y0, n0);
             tma_store_commit();
-            tma_store_wait_read<1>();          // the other output buffer is no longer being read
           }
-          named_bar_sync(2, kEpiThreads);
-          obuf ^= 1u;
         }
       }
       tc_fence_before();
