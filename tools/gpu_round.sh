@@ -23,3 +23,9 @@ if [ "$1" = "ncu" ]; then
       python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_tail.log 2>&1
   echo "ncu full tail exit=$?" | tee -a gpurun_out/summary.txt
 fi
+if [ "$1" = "traffic" ] || [ "$2" = "traffic" ]; then
+  # DRAM bytes of every launch of one step (metrics pass, no --set full): roofline.traffic of bench.py
+  timeout -s KILL 900 ncu --nvtx --nvtx-include "df3d_step/" --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+      --clock-control none --csv --log-file gpurun_out/traffic.csv python bench.py --profile --steps 1 --warmup 3 > gpurun_out/ncu_traffic.log 2>&1
+  echo "ncu traffic exit=$? lines=$(wc -l < gpurun_out/traffic.csv)" | tee -a gpurun_out/summary.txt
+fi
