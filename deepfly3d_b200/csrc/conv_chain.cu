@@ -13,8 +13,8 @@
 //   warp 1  leader CTA (rank 0): MMA issuer; both CTAs: TMEM owner (warp-uniform loop, one elected lane issues)
 //   warp 2  TMA producer of the residual slabs (64 channels x 128 pixels, + the half-resolution slab
 //           of the up-sample branch), a ring that prefetches across stages and tiles
-//   warp 3  idle.  Warps 0..3 (warpgroup 0) give registers back (setmaxnreg 56) so that the epilogue
-//           warpgroups can take 224 each: the heavy epilogues spilled at the 168 registers a 384-thread
+//   warp 3  idle.  Warps 0..3 (warpgroup 0) give registers back (setmaxnreg 104) so that the epilogue
+//           warpgroups can take 200 each: the heavy epilogues spilled at the 168 registers a 384-thread
 //           block allows, and with 227 KB of shared memory (no L1) a spill reload is an L2 round trip
 //   warps 4..11  epilogue: two groups of four warps (one TMEM lane quarter each), group g takes the
 //           64-channel slabs sl = g, g+2 of every stage
@@ -108,102 +108,126 @@ __device__ __forceinline__ float2 bf2_unpack(uint32_t x) { return make_float2(bf
 
 // Operands of one group of 8 channels of a slab, fetched from shared memory two groups ahead of their use
 // (unused members are dead code in the specialisations that do not need them).
+// Per-channel constants of one group of 8 channels (unused members are dead code in the specialisations
+// that do not need them).
 struct EpiGroup {
   float4 sc1[2], sh1[2], sc2[2], sh2[2];
-  uint4 res, up;
+  uint4 res[2], up[2];  // residual / half-resolution residual chunk of the two rows
+};
+// What the epilogue needs to know about one of the two pixel rows a lane works on
+struct EpiRow {
+  const uint8_t* rrow;   // residual slab row (generic pointer), 128 bytes, 16-byte chunks swizzled with sw
+  const uint8_t* rrow2;  // row of the parent pixel in the half-resolution slab, swizzled with sw2
+  uint32_t rrow_s;       // shared-memory address of rrow (in-place output)
+  uint32_t sw, sw2;
+  uint8_t* out;          // global address of this pixel's 64 channels of the slab (stages stored from registers)
+  bool store;
 };
 
-// Epilogue of one 64-channel slab of one stage for one pixel row (one thread), fully specialised:
+// Epilogue of one 64-channel slab of one stage, fully specialised:
 //   UNIT  scale1 == 1 (conv without a folded BatchNorm): v = acc + shift1
 //   RES   + residual (bf16, swizzled slab row)     RES2  + nearest-x2 up-sampled half-resolution residual
 //   RELU  relu after the adds                      XSRC  0: no operand, 1: bf16(v), 2: relu(bn2(bf16(v)))
 //   OUT   bf16(v) to global memory
-// t_slab: TMEM address of the slab's 64 fp32 accumulator columns (the operand is written back in place
-// over the first 32); c1/c2: this slab's first channel in the constant arrays.
-// Software pipeline (measured: the straight version issued 1 instruction in 4 cycles, half of the stalls on
-// shared-memory loads, a quarter behind tcgen05.ld): the slab is four quarters of 16 columns; the
-// tcgen05.ld of quarter q+1 is in flight while quarter q is processed, and the constants / residual rows of
-// group j+2 are loaded before group j is computed.
+// Lane mapping (tcgen05.ld/st shape .16x32bx2): lanes l and l + 16 of a warp share a pixel row and split
+// its channels -- lane l owns channels [32 h, 32 h + 32) of the slab, h = l / 16, for the TWO rows
+// r16 = l % 16 and r16 + 16 of the warp's 32-row quarter.  With the plain .32x32b shape (one row, all 64
+// channels per lane) every lane needs every per-channel constant of the slab, and broadcast loads do not
+// come cheaper: an LDS.128 of one address still costs four shared-memory wavefronts -- the constants were
+// 4 500 of the 9 500 wavefronts per tile on the shared-memory port that bounds this kernel.  Two rows per
+// lane halve that (each constant is fetched once and used for both rows); the residual / output chunks
+// stay 16 bytes per access.
+// t_slab: TMEM address (lane field = first lane of the quarter) of the slab's 64 fp32 accumulator columns;
+// the operand of the next stage is written back in place over the first 32 of them (x_addr), which is
+// safe because both rows' accumulators are in registers before the first tcgen05.st.
+// c1/h1/c2/h2: the constant arrays at this lane's first channel.
 template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT>
 __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restrict__ sc1,
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
-                                         const float4* __restrict__ sh2, const uint8_t* __restrict__ rrow,
-                                         const uint8_t* __restrict__ rrow2, uint32_t sw, uint32_t sw2, uint32_t x_addr,
-                                         uint8_t* out, bool store, uint32_t rrow_s) {
-  auto fetch = [&](EpiGroup& g, int j) {  // j: group of 8 channels, 0..7
+                                         const float4* __restrict__ sh2, const EpiRow (&row)[2], uint32_t x_addr,
+                                         uint32_t h) {
+  auto fetch = [&](EpiGroup& g, int j) {  // j: group of 8 channels of this lane's half, 0..3
     g.sh1[0] = sh1[2 * j];
     g.sh1[1] = sh1[2 * j + 1];
     if (!UNIT) {
       g.sc1[0] = sc1[2 * j];
       g.sc1[1] = sc1[2 * j + 1];
     }
-    if (RES) g.res = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)j ^ sw) << 4));
-    if (RES2) g.up = *reinterpret_cast<const uint4*>(rrow2 + (((uint32_t)j ^ sw2) << 4));
     if (XSRC == 2) {
       g.sc2[0] = sc2[2 * j];
       g.sc2[1] = sc2[2 * j + 1];
       g.sh2[0] = sh2[2 * j];
       g.sh2[1] = sh2[2 * j + 1];
     }
+    const uint32_t ck = 4u * h + (uint32_t)j;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (RES) g.res[w] = *reinterpret_cast<const uint4*>(row[w].rrow + ((ck ^ row[w].sw) << 4));
+      if (RES2) g.up[w] = *reinterpret_cast<const uint4*>(row[w].rrow2 + ((ck ^ row[w].sw2) << 4));
+    }
   };
-  EpiGroup g[3];
-  uint32_t acc[2][16];
-  tmem_ld_32x16(t_slab, acc[0]);
+  uint32_t acc[2][32];
+  tmem_ld_16x32bx2_x32(t_slab, acc[0]);                 // rows r16:      this lane's 32 channels
+  tmem_ld_16x32bx2_x32(t_slab + (16u << 16), acc[1]);   // rows r16 + 16
+  EpiGroup g[2];
+  uint32_t held[2][4];  // stages stored from registers: the even group's 16 bytes wait for the odd group's
+  (void)held;
   fetch(g[0], 0);
-  fetch(g[1], 1);
+  tmem_ld_wait();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    tmem_ld_wait();
-    if (q + 1 < 4) tmem_ld_32x16(t_slab + (q + 1) * 16, acc[(q + 1) & 1]);
-    uint32_t op[8], xp[8];
+  for (int j = 0; j < 4; ++j) {
+    if (j + 1 < 4) fetch(g[(j + 1) & 1], j + 1);
+    const EpiGroup& G = g[j & 1];
+    const float2 t1[4] = {make_float2(G.sh1[0].x, G.sh1[0].y), make_float2(G.sh1[0].z, G.sh1[0].w),
+                          make_float2(G.sh1[1].x, G.sh1[1].y), make_float2(G.sh1[1].z, G.sh1[1].w)};
+    const float2 s1[4] = {make_float2(G.sc1[0].x, G.sc1[0].y), make_float2(G.sc1[0].z, G.sc1[0].w),
+                          make_float2(G.sc1[1].x, G.sc1[1].y), make_float2(G.sc1[1].z, G.sc1[1].w)};
+    const float2 s2[4] = {make_float2(G.sc2[0].x, G.sc2[0].y), make_float2(G.sc2[0].z, G.sc2[0].w),
+                          make_float2(G.sc2[1].x, G.sc2[1].y), make_float2(G.sc2[1].z, G.sc2[1].w)};
+    const float2 t2[4] = {make_float2(G.sh2[0].x, G.sh2[0].y), make_float2(G.sh2[0].z, G.sh2[0].w),
+                          make_float2(G.sh2[1].x, G.sh2[1].y), make_float2(G.sh2[1].z, G.sh2[1].w)};
+    const uint32_t chunk = 4u * h + (uint32_t)j;  // 16-byte chunk of the 128-byte slab row
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = 2 * q + h;
-      if (j + 2 < 8) fetch(g[(j + 2) % 3], j + 2);
-      const EpiGroup& G = g[j % 3];
-      const uint32_t* a = acc[q & 1] + 8 * h;
-      const float2 t1[4] = {make_float2(G.sh1[0].x, G.sh1[0].y), make_float2(G.sh1[0].z, G.sh1[0].w),
-                            make_float2(G.sh1[1].x, G.sh1[1].y), make_float2(G.sh1[1].z, G.sh1[1].w)};
-      const float2 s1[4] = {make_float2(G.sc1[0].x, G.sc1[0].y), make_float2(G.sc1[0].z, G.sc1[0].w),
-                            make_float2(G.sc1[1].x, G.sc1[1].y), make_float2(G.sc1[1].z, G.sc1[1].w)};
-      const uint32_t rw[4] = {G.res.x, G.res.y, G.res.z, G.res.w};
-      const uint32_t uw[4] = {G.up.x, G.up.y, G.up.z, G.up.w};
-      float2 v[4];
+    for (int w = 0; w < 2; ++w) {
+      const EpiRow& R = row[w];
+      const uint32_t rw[4] = {G.res[w].x, G.res[w].y, G.res[w].z, G.res[w].w};
+      const uint32_t uw[4] = {G.up[w].x, G.up[w].y, G.up[w].z, G.up[w].w};
+      const uint32_t* a = acc[w] + 8 * j;
+      uint32_t op[4], xp[4];
+      (void)xp;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 ac = make_float2(__uint_as_float(a[2 * e]), __uint_as_float(a[2 * e + 1]));
-        v[e] = UNIT ? fadd2(ac, t1[e]) : ffma2(ac, s1[e], t1[e]);
-        if (RES) v[e] = fadd2(v[e], bf2_unpack(rw[e]));
+        float2 v = UNIT ? fadd2(ac, t1[e]) : ffma2(ac, s1[e], t1[e]);
+        if (RES) v = fadd2(v, bf2_unpack(rw[e]));
         if (RES2)  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
-          v[e] = fadd2(bf2_unpack(pack2(v[e].x, v[e].y)), bf2_unpack(uw[e]));
-        op[4 * h + e] = RELU ? pack2_relu(v[e].x, v[e].y) : pack2(v[e].x, v[e].y);
-      }
-      if (XSRC == 2) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
-        const float2 s2[4] = {make_float2(G.sc2[0].x, G.sc2[0].y), make_float2(G.sc2[0].z, G.sc2[0].w),
-                              make_float2(G.sc2[1].x, G.sc2[1].y), make_float2(G.sc2[1].z, G.sc2[1].w)};
-        const float2 t2[4] = {make_float2(G.sh2[0].x, G.sh2[0].y), make_float2(G.sh2[0].z, G.sh2[0].w),
-                              make_float2(G.sh2[1].x, G.sh2[1].y), make_float2(G.sh2[1].z, G.sh2[1].w)};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 x = ffma2(bf2_unpack(op[4 * h + e]), s2[e], t2[e]);
-          xp[4 * h + e] = pack2_relu(x.x, x.y);
+          v = fadd2(bf2_unpack(pack2(v.x, v.y)), bf2_unpack(uw[e]));
+        op[e] = RELU ? pack2_relu(v.x, v.y) : pack2(v.x, v.y);
+        if (XSRC == 2) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
+          const float2 x = ffma2(bf2_unpack(op[e]), s2[e], t2[e]);
+          xp[e] = pack2_relu(x.x, x.y);
         }
       }
-    }
-    if (XSRC == 1) tmem_st_32x8(x_addr + q * 8, op);
-    if (XSRC == 2) tmem_st_32x8(x_addr + q * 8, xp);
-    if (OUT && RES) {
-      // Stored stage with a residual: bf16(v) replaces the residual it was computed from, in place in the
-      // slab (this thread read those two chunks two groups ago); the warp's 32 rows then leave with one TMA
-      // store (run_stage).  256-bit stores from registers, one pixel row per lane, cost the LSU data pipe
-      // ~50 wavefronts per instruction (measured: 4 900 of the 9 500 LSU wavefronts of a tile).
-      sts128(rrow_s + (((uint32_t)(2 * q) ^ sw) << 4), make_uint4(op[0], op[1], op[2], op[3]));
-      sts128(rrow_s + (((uint32_t)(2 * q + 1) ^ sw) << 4), make_uint4(op[4], op[5], op[6], op[7]));
-    } else if (OUT) {
-      // 16 channels = 32 contiguous bytes of this thread's pixel: one full sector.  (Staging the slab in shared
-      // memory for one TMA store was measured too: the stores leave the warps' issue path, but the 32 KB of
-      // staging cost two slots of the weight ring or a residual slab, and either loss outweighs the gain.)
-      if (store) stg256(out + q * 32, op);
+      // 8 channels = 4 packed operand columns: lanes < 16 write columns [4 j, 4 j + 4), the others 16 further
+      if (XSRC == 1) tmem_st_16x32bx2_x4(x_addr + ((uint32_t)(16 * w) << 16) + 4 * j, op);
+      if (XSRC == 2) tmem_st_16x32bx2_x4(x_addr + ((uint32_t)(16 * w) << 16) + 4 * j, xp);
+      if (OUT && RES) {
+        // Stored stage with a residual: bf16(v) replaces the residual chunk it was computed from, in place in
+        // the slab; the warp's 32 rows then leave with one TMA store (run_stage).  256-bit stores from
+        // registers cost the LSU data pipe ~50 wavefronts per instruction (measured: 4 900 of 9 500 per tile).
+        sts128(R.rrow_s + ((chunk ^ R.sw) << 4), make_uint4(op[0], op[1], op[2], op[3]));
+      } else if (OUT) {
+        // two groups = 16 channels = 32 contiguous bytes of this pixel: one full sector per store.  (Staging in
+        // shared memory for a TMA store was measured too: the 32 KB of staging cost two slots of the weight
+        // ring or a residual slab.)
+        if ((j & 1) == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) held[w][e] = op[e];
+        } else if (R.store) {
+          const uint32_t both[8] = {held[w][0], held[w][1], held[w][2], held[w][3], op[0], op[1], op[2], op[3]};
+          stg256(R.out + ((chunk - 1u) << 4), both);
+        }
+      }
     }
   }
 }
@@ -336,8 +360,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   };
 
   // register re-allocation between the warpgroups, inside the role branches so that ptxas budgets each role
-  // separately (per scheduler: 120 + 2 x 192 = 504 of 512 registers per lane)
-  if (warp < kEpiWarp0c) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+  // separately (per scheduler: 104 + 2 x 200 = 504 registers per lane = the 3 x 168 the CTA was launched with: setmaxnreg moves registers inside the CTA's own pool, a larger sum blocks forever)
+  if (warp < kEpiWarp0c) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // ------------------------------------------------------------------ ring producer (issue order of the MMA warp)
     if (lane == 0) {
@@ -613,21 +637,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   } else if (warp >= kEpiWarp0c) {
     // ------------------------------------------------------------------ epilogue (warps 4..11)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int grp = (warp - kEpiWarp0c) >> 2; // slab parity this group handles
-    const int m = q * 32 + lane;              // row of the tile = pixel
-    const uint32_t row_off = (uint32_t)m * 128u;
-    const uint32_t sw = (uint32_t)(m & 7);
+    // two pixel rows per lane (see epi_slab): lanes l and l + 16 share rows r16 and r16 + 16 of the quarter
+    const uint32_t h = (uint32_t)lane >> 4;   // which 32 of a slab's 64 channels this lane owns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    // position of this thread's pixel inside the tile, and the row of its parent in the
-    // half-resolution residual slab (box tw/2 x th/2 x nb)
-    const int pw = m % p.tw, phh = (m / p.tw) % p.th, pn = m / (p.tw * p.th);
-    uint32_t row2_off, sw2;
-    {
-      const int r2 = (pn * (p.th >> 1) + (phh >> 1)) * (p.tw >> 1) + (pw >> 1);
-      row2_off = (uint32_t)r2 * 128u;
-      sw2 = (uint32_t)(r2 & 7);
+    uint32_t row_off[2], sw[2], row2_off[2], sw2[2];
+    int pw[2], phh[2], pn[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int m = q * 32 + 16 * w + (lane & 15);  // row of the tile = pixel
+      row_off[w] = (uint32_t)m * 128u;
+      sw[w] = (uint32_t)(m & 7);
+      // position of the pixel inside the tile, and the row of its parent in the half-resolution residual slab
+      // (box tw/2 x th/2 x nb)
+      pw[w] = m % p.tw;
+      phh[w] = (m / p.tw) % p.th;
+      pn[w] = m / (p.tw * p.th);
+      const int r2 = (pn[w] * (p.th >> 1) + (phh[w] >> 1)) * (p.tw >> 1) + (pw[w] >> 1);
+      row2_off[w] = (uint32_t)r2 * 128u;
+      sw2[w] = (uint32_t)(r2 & 7);
     }
     // this warp's quarter of the tile (32 consecutive pixels) as a TMA sub-box: offsets inside the tile
     const int rpq = 32 / p.tw;  // rows per quarter
@@ -643,12 +673,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // epilogue of stage i of the tile (local number t) at pixel offsets x0, y0, n0
     auto run_stage = [&](int i, int t, int x0, int y0, int n0) {
       const StageLite& st = lite(i);
-      const bool in_batch = (n0 + pn) < p.B && !(p.dbg_exec & 2);  // partially filled multi-image tiles: skip the stores
-      const size_t pixel = ((size_t)(n0 + pn) * p.H + (y0 + phh)) * p.W + (x0 + pw);
       const bool has_res = st.has_res != 0;
       const int x_src = st.x_src, kind = st.kind;
       const int nsl = st.n >> 6;
-      uint8_t* const out_row = st.out ? reinterpret_cast<uint8_t*>(st.out) + pixel * (size_t)st.n * 2 : nullptr;
+      bool in_batch[2];
+      uint8_t* out_row[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        in_batch[w] = (n0 + pn[w]) < p.B && !(p.dbg_exec & 2);  // partially filled multi-image tiles: skip the stores
+        const size_t pixel = ((size_t)(n0 + pn[w]) * p.H + (y0 + phh[w])) * p.W + (x0 + pw[w]);
+        out_row[w] = st.out ? reinterpret_cast<uint8_t*>(st.out) + pixel * (size_t)st.n * 2 : nullptr;
+      }
       const float4* const sc1 = reinterpret_cast<const float4*>(sm + (aff_base - smem_base)) + (st.aff_off >> 2);
       const float4* const sh1 = sc1 + (st.unit ? 0 : (st.n >> 2));
       const float4* const sc2 = sh1 + (st.n >> 2);
@@ -673,20 +708,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           mbar_wait_warp(sfull(su), sph);
           slab = s_base + su * (uint32_t)p.slab_bytes;
         }
-        const uint32_t rrow_s = slab + row_off;
-        const uint8_t* const rrow = sm + (slab - smem_base) + row_off;
-        const uint8_t* const rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off;
-        const float4 *c1 = sc1 + sl * 16, *h1 = sh1 + sl * 16, *c2 = sc2 + sl * 16, *h2 = sh2 + sl * 16;
-        uint8_t* const o = out_row + sl * 128;
+        EpiRow row[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          row[w].rrow_s = slab + row_off[w];
+          row[w].rrow = sm + (slab - smem_base) + row_off[w];
+          row[w].rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off[w];
+          row[w].sw = sw[w];
+          row[w].sw2 = sw2[w];
+          row[w].out = out_row[w] + sl * 128;
+          row[w].store = in_batch[w];
+        }
+        // constants of this lane's 32 channels of the slab (float4 units)
+        const float4 *c1 = sc1 + sl * 16 + h * 8, *h1 = sh1 + sl * 16 + h * 8, *c2 = sc2 + sl * 16 + h * 8,
+                     *h2 = sh2 + sl * 16 + h * 8;
         // the operand of the next stage replaces the first 32 of the 64 columns just read (in place)
         switch (kind) {  //          UNIT   RES    RES2   RELU  XSRC OUT
-          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
-          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, rrow, rrow2, sw, sw2, t_slab, o, in_batch, rrow_s); break;
+          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
+          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
           default: break;  // launch_conv_chain rejects anything else
         }
         if (has_res && st.out) {
