@@ -116,9 +116,9 @@ struct EpiGroup {
 };
 // What the epilogue needs to know about one of the two pixel rows a lane works on
 struct EpiRow {
-  const uint8_t* rrow;   // residual slab row (generic pointer), 128 bytes, 16-byte chunks swizzled with sw
-  const uint8_t* rrow2;  // row of the parent pixel in the half-resolution slab, swizzled with sw2
-  uint32_t rrow_s;       // shared-memory address of rrow (in-place output)
+  uint32_t rrow_s;       // residual slab row (shared-memory address), 128 bytes, 16-byte chunks swizzled with sw;
+                         // also where the in-place output goes
+  uint32_t rrow2_s;      // row of the parent pixel in the half-resolution slab, swizzled with sw2
   uint32_t sw, sw2;
   uint8_t* out;          // global address of this pixel's 64 channels of the slab (stages stored from registers)
   bool store;
@@ -146,6 +146,9 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
                                          const float4* __restrict__ sh2, const EpiRow (&row)[2], uint32_t x_addr,
                                          uint32_t h) {
+  // (sc1 .. sh2 are pointers derived from a __shared__ array: the compiler emits LDS for them directly; the
+  // slab rows are 32-bit shared addresses -- a generic pointer rebuilt per slab cost an S2UR of the cluster
+  // CTA id and a dependent address chain each time)
   auto fetch = [&](EpiGroup& g, int j) {  // j: group of 8 channels of this lane's half, 0..3
     g.sh1[0] = sh1[2 * j];
     g.sh1[1] = sh1[2 * j + 1];
@@ -162,8 +165,8 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
     const uint32_t ck = 4u * h + (uint32_t)j;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      if (RES) g.res[w] = *reinterpret_cast<const uint4*>(row[w].rrow + ((ck ^ row[w].sw) << 4));
-      if (RES2) g.up[w] = *reinterpret_cast<const uint4*>(row[w].rrow2 + ((ck ^ row[w].sw2) << 4));
+      if (RES) g.res[w] = lds128(row[w].rrow_s + ((ck ^ row[w].sw) << 4));
+      if (RES2) g.up[w] = lds128(row[w].rrow2_s + ((ck ^ row[w].sw2) << 4));
     }
   };
   uint32_t acc[2][32];
@@ -232,6 +235,9 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
   }
 }
 
+// kProbe: the time-stamp probe of tools/chain_probe.cu (launch_conv_chain picks that instantiation when
+// ChainParams::dbg is set); the production instantiation carries none of its branches.
+template <bool kProbe>
 __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint32_t d0 = tmem_base + (uint32_t)p.st[0].col[0], d1 = tmem_base + (uint32_t)p.st[0].col[1];
     const int hz0 = p.st[0].hz_stage, hz0_delta = p.st[0].hz_delta;
     uint32_t mu = 0, mph = 0;
-    unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+    unsigned long long* const dbg = (kProbe && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
     int di = 0;
 
     // Ring consumption with the barrier latency taken off the issue path: the readiness of the NEXT slot is
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint64_t desc_halo = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32);  // group pitch
     uint32_t heads = 0;
     auto issue_head = [&](int t) {
-      if (dbg && di < 4000) dbg[di++] = clock64();  // [head start]
+      if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [head start]
       if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait_cluster(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
       if (p.halo) {
         // A operand of tap (dy, dx) = the halo rows shifted by dy*10 + dx: pixel (r, c) of the 8-wide tile is
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           umma_commit_pair(hempty);  // the halo may be overwritten once these MMAs retire
           umma_commit_pair(accfull(0));
         }
-        if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
+        if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
         return;
       }
 #pragma unroll 1
@@ -572,7 +578,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         ring_advance();
       }
       if (elect_one()) umma_commit_pair(accfull(0));
-      if (dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
+      if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [head issued]
     };
 
     // later stage i of local tile t: A from tensor memory (written in place by the previous epilogue), B from the ring
@@ -587,7 +593,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_wait_cluster(epidone(i - 1), par);  // operand of this stage is complete in tensor memory (both CTAs)
       if (hz >= 0 && t - hzd >= 0) mbar_wait_cluster(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
       tc_fence_after();
-      if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
+      if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
       const int slots = (kbn * nh) >> 1;
 #pragma unroll 1
       for (int sl = 0; sl < slots; ++sl) {
@@ -615,10 +621,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         ring_advance();
       }
       if (elect_one()) umma_commit_pair(accfull(i));  // accumulator ready; the consumed operand may be overwritten
-      if (dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
-      if (p.dbg_exec & 1) {  // probe only: how long until the accumulator is complete (serialises this warp)
+      if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [stage i issued]
+      if (kProbe && (p.dbg_exec & 1)) {  // probe only: how long until the accumulator is complete (serialises this warp)
         mbar_wait_cluster(accfull(i), par);
-        if (dbg && di < 4000) dbg[di++] = clock64();
+        if (kProbe && dbg && di < 4000) dbg[di++] = clock64();
       }
     };
 
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     uint32_t pending = kNoSlab;     // lane 0: slab whose TMA store may still be reading it
     uint32_t spos = 0, sphase = 0;  // ring position / phase of the next residual slab (slab 0 of the next stage with one)
     const uint32_t n_slabs = (uint32_t)p.n_slabs;
-    unsigned long long* const dbg = (blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
+    unsigned long long* const dbg = (kProbe && blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
     int di = 4096 * (1 + grp);
     const int dend = di + 4000;
 
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       uint8_t* out_row[2];
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        in_batch[w] = (n0 + pn[w]) < p.B && !(p.dbg_exec & 2);  // partially filled multi-image tiles: skip the stores
+        in_batch[w] = (n0 + pn[w]) < p.B && !(kProbe && (p.dbg_exec & 2));  // partially filled multi-image tiles: skip the stores
         const size_t pixel = ((size_t)(n0 + pn[w]) * p.H + (y0 + phh[w])) * p.W + (x0 + pw[w]);
         out_row[w] = st.out ? reinterpret_cast<uint8_t*>(st.out) + pixel * (size_t)st.n * 2 : nullptr;
       }
@@ -688,11 +694,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const float4* const sh1 = sc1 + (st.unit ? 0 : (st.n >> 2));
       const float4* const sc2 = sh1 + (st.n >> 2);
       const float4* const sh2 = sc2 + (st.n >> 2);
-      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i entered]
+      if (kProbe && dbg && di < dend) dbg[di++] = clock64();  // [stage i entered]
       if (lane == 0) mbar_wait_cluster(accfull(i), (uint32_t)t & 1u);  // one polling lane (see mbar_wait_warp)
       __syncwarp();
       tc_fence_after();
-      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
+      if (kProbe && dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
       const uint32_t t_lo = tmem_base + lane_base + (uint32_t)st.col0, t_hi = tmem_base + lane_base + (uint32_t)st.col1;
 #pragma unroll 1
       for (int sl = grp; sl < nsl; sl += 2) {
@@ -712,8 +718,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           row[w].rrow_s = slab + row_off[w];
-          row[w].rrow = sm + (slab - smem_base) + row_off[w];
-          row[w].rrow2 = sm + (slab - smem_base) + kUnitBytes + row2_off[w];
+          row[w].rrow2_s = slab + kUnitBytes + row2_off[w];
           row[w].sw = sw[w];
           row[w].sw2 = sw2[w];
           row[w].out = out_row[w] + sl * 128;
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(p.dbg_exec & 2)) tma_store_4d(&p.st[i].tmOutQ, slab + (uint32_t)q * 4096u, sl * 64, x0 + qx, y0 + qy, n0 + qn);
+            if (!(kProbe && (p.dbg_exec & 2))) tma_store_4d(&p.st[i].tmOutQ, slab + (uint32_t)q * 4096u, sl * 64, x0 + qx, y0 + qy, n0 + qn);
             tma_store_commit();
             if (pending != kNoSlab) {
               tma_store_wait_read<1>();
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         mbar_arrive(sempty(pending));
         pending = kNoSlab;
       }
-      if (dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
+      if (kProbe && dbg && di < dend) dbg[di++] = clock64();  // [stage i epilogue done]
     };
 
     int x0 = 0, y0 = 0, n0 = 0;
@@ -811,7 +816,8 @@ int make_tmap_quarter(CUtensorMap* out, const void* base, int C, int W, int H, i
 }
 
 int conv_chain_configure() {
-  DF3D_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemLimit));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemLimit));
+  DF3D_CUDA(cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemLimit));
   return DF3D_OK;
 }
 
@@ -981,7 +987,11 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DF3D_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, p));
+  if (p.dbg) {
+    DF3D_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, p));
+  } else {
+    DF3D_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, p));
+  }
   DF3D_LAUNCH_CHECK("conv_chain_kernel");
   return DF3D_OK;
 }
