@@ -7,8 +7,9 @@
                             network frame
     conf     (7, T, 19, 1)  float32 peak value
 
-Image ingest (JPEG decode + resize on the host) is the reference's path too and is not part of
-the accelerated hot path.
+Image ingest: the JPEG files are decoded on the host (the reference's path too; SURVEY.md section 8(f)
+row 1); the resize to the network input runs on the device (csrc/ingest.cu, bit-identical to the
+cv2.resize(..., INTER_LINEAR) the loader used to do on the host).
 """
 import os
 
@@ -28,26 +29,39 @@ def image_name(folder, cam_id, img_id):
     return os.path.join(folder, f"camera_{cam_id}_img_{img_id:06d}.jpg")
 
 
-def load_images(folder, max_img_id, size_hw, pin_memory=True):
-    """-> uint8 tensor (7, T, H, W) gray, resized to the network input."""
+def read_images(folder, max_img_id, pin_memory=True):
+    """-> uint8 tensor (7, T, Hs, Ws): the gray frames at their native size, in pinned host memory."""
     import cv2
 
     T = max_img_id + 1
-    H, W = size_hw
-    out = torch.empty((NUM_CAMERAS, T, H, W), dtype=torch.uint8)
-    if pin_memory and torch.cuda.is_available():
-        out = out.pin_memory()
-    arr = out.numpy()
+    out = None
     for c in range(NUM_CAMERAS):
         for t in range(T):
             path = image_name(folder, c, t)
             img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
             if img is None:
                 raise FileNotFoundError(f"cannot read {path}")
-            if img.shape != (H, W):
-                img = cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR)
+            if out is None:
+                out = torch.empty((NUM_CAMERAS, T) + img.shape, dtype=torch.uint8)
+                if pin_memory and torch.cuda.is_available():
+                    out = out.pin_memory()
+                arr = out.numpy()
+            if img.shape != tuple(out.shape[2:]):
+                raise ValueError(f"{path}: image size {img.shape} differs from the first image {tuple(out.shape[2:])}")
             arr[c, t] = img
     return out
+
+
+def load_images(folder, max_img_id, size_hw, pin_memory=True, device="cuda"):
+    """-> uint8 tensor (7*T, H, W) gray ON THE DEVICE, resized to the network input (camera-major)."""
+    from . import ops
+
+    native = read_images(folder, max_img_id, pin_memory=pin_memory)
+    C, T, Hs, Ws = native.shape
+    dev = native.reshape(C * T, Hs, Ws).to(device, non_blocking=True)
+    if (Hs, Ws) != tuple(size_hw):
+        dev = ops.resize_gray_u8(dev, size_hw)
+    return dev
 
 
 def random_state_dict(num_stacks=2, num_classes=NUM_PREDICT, seed=0):
@@ -118,7 +132,7 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     Hh, Wh = HEATMAP_SHAPE
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
-    images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory)
+    dev_images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory, device=device)
     sd = state_dict if state_dict is not None else load_state_dict(weights)
     # batch_size is the reference's DataLoader batch; here the whole folder is one device batch and
     # the engine chunks internally, so it only bounds the workspace for tiny folders
@@ -126,7 +140,6 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     flip = torch.zeros((NUM_CAMERAS, T), dtype=torch.uint8)
     for c in camera_ids_to_flip:
         flip[int(c)] = 1
-    dev_images = images.reshape(NUM_CAMERAS * T, in_h, in_w).to(device, non_blocking=True)
     res = eng.forward(dev_images, flip=flip.reshape(-1).to(device), return_heatmap=return_heatmap)
     idx, conf = res[0], res[1]
     idx_h = idx.cpu().numpy().astype(np.int64).reshape(NUM_CAMERAS, T, -1)

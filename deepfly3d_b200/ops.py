@@ -51,6 +51,20 @@ def heatmap_argmax_nhwc(hm, K):
     return idx, conf
 
 
+def resize_gray_u8(images, size_hw):
+    """images (B,Hs,Ws) uint8 on the device -> (B,Hd,Wd) uint8, bit-identical to
+    cv2.resize(img, (Wd, Hd), interpolation=cv2.INTER_LINEAR) per image (the loader's host path)."""
+    _need_cuda(images)
+    if images.dtype != torch.uint8 or images.dim() != 3:
+        raise ValueError("resize_gray_u8: expected a (B, H, W) uint8 tensor")
+    images = images.contiguous()
+    B, Hs, Ws = images.shape
+    Hd, Wd = int(size_hw[0]), int(size_hw[1])
+    out = torch.empty((B, Hd, Wd), dtype=torch.uint8, device=images.device)
+    check(lib.df3d_resize_gray_u8(_ptr(images), B, Hs, Ws, _ptr(out), Hd, Wd, _stream()))
+    return out
+
+
 def pack_points2d(idx, C_, T, heatmap_shape, camera_ordering, image_shape):
     """idx (C*T,K) int32 (camera-major) -> points2d (C,T,2K,2) f64 normalised (row,col),
     pts_xy (C,T,2K,2) f64 pixel (x,y).  image_shape = [W, H] like Core.image_shape."""

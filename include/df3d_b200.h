@@ -60,6 +60,18 @@ int df3d_heatmap_argmax_nhwc(const float* hm_dev, int B, int H, int W, int Cpad,
                              int32_t* idx_dev, float* conf_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Image ingest: bilinear resize of uint8 gray images to the network input on the device.
+ * Replaces the cv2.resize(img, (Wd, Hd), interpolation=INTER_LINEAR) of the image loader in front of
+ * df2d.inference.inference_folder (call site df3d/core.py:177-185); bit-identical to OpenCV's
+ * fixed-point algorithm for 8-bit images.
+ *
+ *   src_dev : (B, Hs, Ws) uint8, images contiguous
+ *   dst_dev : (B, Hd, Wd) uint8; Wd a multiple of 4, 4-byte aligned
+ * ------------------------------------------------------------------------------------------ */
+int df3d_resize_gray_u8(const uint8_t* src_dev, int B, int Hs, int Ws, uint8_t* dst_dev, int Hd, int Wd,
+                        void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * 19 -> 38 joint packing.  Replaces df3d/core.py:187-203 (Core.pose2d_estimation after
  * inference_folder) and the pixel scaling of core.py:247 (`points2d * image_shape[::-1]`).
  *

@@ -1,0 +1,54 @@
+"""GPU parity of the device-side image resize (csrc/ingest.cu) through the C ABI: bit-exact against the CPU
+oracle (oracle/ingest.py, itself pinned to cv2.resize in test_oracle_ingest.py) and against cv2 directly, and
+the loader end to end on the reference's sample frames."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.ingest import resize_bilinear_u8
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test needs a CUDA device")
+    from deepfly3d_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.mark.parametrize("shape", [(3, 480, 960, 256, 512), (2, 480, 960, 256, 256), (5, 128, 128, 256, 256),
+                                   (1, 77, 131, 64, 64), (2, 512, 512, 256, 256), (1, 33, 47, 256, 512),
+                                   (2, 480, 960, 480, 960), (0, 16, 16, 8, 8)])
+def test_resize_bit_exact(ops, shape):
+    B, hs, ws, hd, wd = shape
+    rng = np.random.default_rng(B * 7 + hs + wd)
+    img = rng.integers(0, 256, (B, hs, ws), dtype=np.uint8)
+    got = ops.resize_gray_u8(torch.as_tensor(img).cuda(), (hd, wd)).cpu().numpy()
+    assert got.shape == (B, hd, wd)
+    for b in range(B):
+        assert np.array_equal(got[b], resize_bilinear_u8(img[b], (hd, wd)))
+
+
+def test_resize_matches_cv2_on_reference_frames(ops):
+    cv2 = pytest.importorskip("cv2")
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "images", "*.jpg")))[:14]
+    imgs = np.stack([cv2.imread(f, cv2.IMREAD_GRAYSCALE) for f in files])
+    got = ops.resize_gray_u8(torch.as_tensor(imgs).cuda(), (256, 512)).cpu().numpy()
+    for b in range(len(files)):
+        assert np.array_equal(got[b], cv2.resize(imgs[b], (512, 256), interpolation=cv2.INTER_LINEAR))
+
+
+def test_resize_rejects_bad_arguments(ops):
+    x = torch.zeros((1, 8, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.resize_gray_u8(x, (8, 6))          # output width not a multiple of 4
+    with pytest.raises(ValueError):
+        ops.resize_gray_u8(x.float(), (8, 8))  # wrong dtype
