@@ -264,7 +264,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t hfull = bar_base + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
   const uint32_t hempty = hfull + 8u;
   const uint32_t tmem_slot = hfull + 16u;
-  const StageLite* const lite0 = reinterpret_cast<const StageLite*>(sm + (bar_base - smem_base) + 8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 64);
+  // operand K block sl (= 64-channel slab sl of the stage's output) written to tensor memory by all its warps:
+  // the next stage's MMAs over that K block may go while the epilogue still works on the other slabs
+  auto epislab = [&](uint32_t i, uint32_t sl) { return hfull + 32u + 8u * (4u * i + sl); };
+  const StageLite* const lite0 = reinterpret_cast<const StageLite*>(sm + (bar_base - smem_base) + 8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 32 + 8 * 4 * kMaxChain);
   auto lite = [&](int i) -> const StageLite& { return *reinterpret_cast<const StageLite*>(reinterpret_cast<const uint8_t*>(lite0) + i * kLiteStride); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t lead_bar = mapa_cluster(bar_base, 0);
   auto mfull_l = [&](uint32_t s) { return lead_bar + 8u * s; };
   auto epidone_l = [&](uint32_t i) { return lead_bar + 8u * (2 * kMaxM + 2 * kMaxSlabs + kMaxChain + i); };
+  auto epislab_l = [&](uint32_t i, uint32_t sl) { return lead_bar + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 32u + 8u * (4u * i + sl); };
   const uint32_t hfull_l = lead_bar + 8u * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain);
 
   if (warp == 0 && lane == 0) {
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     for (int i = 0; i < n_chain; ++i) {
       mbar_init(accfull(i), 1);
       mbar_init(epidone(i), 16);  // one arrive per epilogue warp of BOTH CTAs (only the leader's copy is used)
+      for (int sl = 0; sl < 4; ++sl) mbar_init(epislab(i, sl), 8);  // the four warps of the slab's group, both CTAs
     }
     mbar_init(hfull, 1);
     mbar_init(hempty, 1);
@@ -590,13 +595,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const uint32_t c0 = tmem_base + (uint32_t)L.col0, c1 = tmem_base + (uint32_t)L.col1;
       const uint32_t x0c = tmem_base + (uint32_t)Lp.col0, x1c = tmem_base + (uint32_t)Lp.col1;
       const int hz = L.hz, hzd = L.hzd;
-      mbar_wait_cluster(epidone(i - 1), par);  // operand of this stage is complete in tensor memory (both CTAs)
       if (hz >= 0 && t - hzd >= 0) mbar_wait_cluster(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
-      tc_fence_after();
-      if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
       const int slots = (kbn * nh) >> 1;
 #pragma unroll 1
       for (int sl = 0; sl < slots; ++sl) {
+        // the operand K block(s) of this slot are complete in tensor memory (both CTAs): per 64-channel slab of
+        // the previous stage's epilogue, so these MMAs overlap the epilogue of its remaining slabs
+        if (nh == 2) {
+          mbar_wait_cluster(epislab(i - 1, sl), par);
+        } else {
+          mbar_wait_cluster(epislab(i - 1, 2 * sl), par);
+          mbar_wait_cluster(epislab(i - 1, 2 * sl + 1), par);
+        }
+        tc_fence_after();
+        if (kProbe && sl == 0 && dbg && di < 4000) dbg[di++] = clock64();  // [stage i operand ready]
         ring_wait();
         const uint32_t b_addr = m_base + mu * slot_bytes;
         const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
@@ -756,6 +768,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive(sempty(su));
         }
+        if (x_src) {  // this slab = one K block of the next stage's operand: hand it to the MMA warp now
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(epislab_l(i, sl));
+        }
       }
       if (has_res) {
         spos += (uint32_t)nsl;
@@ -764,10 +782,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           sphase ^= 1u;
         }
       }
-      if (x_src) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(epidone_l(i));  // counted on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(epidone_l(i));  // counted on the leader's barrier (accumulator columns drained)
       if (lane == 0 && pending != kNoSlab) {  // after the hand-over to the tensor pipe: release the last stored slab
         tma_store_wait_read<0>();
         mbar_arrive(sempty(pending));
