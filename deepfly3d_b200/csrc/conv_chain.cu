@@ -689,19 +689,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const int dend = di + 4000;
 
     // epilogue of stage i of the tile (local number t) at pixel offsets x0, y0, n0
-    auto run_stage = [&](int i, int t, int x0, int y0, int n0) {
+    // pixel index of this lane's two rows for a tile at (x0, y0, n0), and whether they lie inside the batch
+    // (partially filled multi-image tiles, phantom tiles): once per tile, not per stage
+    struct TilePix {
+      uint32_t pix[2];
+      bool inb[2];
+    };
+    auto tile_pix = [&](int x0, int y0, int n0) {
+      TilePix tp;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        tp.inb[w] = (n0 + pn[w]) < p.B && !(kProbe && (p.dbg_exec & 2));
+        tp.pix[w] = (uint32_t)(((n0 + pn[w]) * p.H + (y0 + phh[w])) * p.W + (x0 + pw[w]));
+      }
+      return tp;
+    };
+    auto run_stage = [&](int i, int t, int x0, int y0, int n0, const TilePix& tp) {
       const StageLite& st = lite(i);
       const bool has_res = st.has_res != 0;
       const int x_src = st.x_src, kind = st.kind;
       const int nsl = st.n >> 6;
-      bool in_batch[2];
       uint8_t* out_row[2];
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        in_batch[w] = (n0 + pn[w]) < p.B && !(kProbe && (p.dbg_exec & 2));  // partially filled multi-image tiles: skip the stores
-        const size_t pixel = ((size_t)(n0 + pn[w]) * p.H + (y0 + phh[w])) * p.W + (x0 + pw[w]);
-        out_row[w] = st.out ? reinterpret_cast<uint8_t*>(st.out) + pixel * (size_t)st.n * 2 : nullptr;
-      }
+      for (int w = 0; w < 2; ++w)
+        out_row[w] = reinterpret_cast<uint8_t*>(st.out) + (size_t)tp.pix[w] * (size_t)(st.n * 2);  // only used when st.out != 0
       const float4* const sc1 = reinterpret_cast<const float4*>(sm + (aff_base - smem_base)) + (st.aff_off >> 2);
       const float4* const sh1 = sc1 + (st.unit ? 0 : (st.n >> 2));
       const float4* const sc2 = sh1 + (st.n >> 2);
@@ -734,21 +745,29 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           row[w].sw = sw[w];
           row[w].sw2 = sw2[w];
           row[w].out = out_row[w] + sl * 128;
-          row[w].store = in_batch[w];
+          row[w].store = tp.inb[w];
         }
         // constants of this lane's 32 channels of the slab (float4 units)
         const float4 *c1 = sc1 + sl * 16 + h * 8, *h1 = sh1 + sl * 16 + h * 8, *c2 = sc2 + sl * 16 + h * 8,
                      *h2 = sh2 + sl * 16 + h * 8;
         // the operand of the next stage replaces the first 32 of the 64 columns just read (in place)
-        switch (kind) {  //          UNIT   RES    RES2   RELU  XSRC OUT
-          case kEpiReluX:     epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiReluOut:   epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiResOutAct: epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiResUpOutAct: epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiResOut:    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiResUpOut:  epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          case kEpiResX:      epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h); break;
-          default: break;  // launch_conv_chain rejects anything else
+        // (a tree of two-way branches on the stage's properties: a switch over `kind` compiles to a jump table in
+        // the constant bank, whose load + indirect branch cost a few hundred cycles per slab when it misses)
+        //                          UNIT   RES    RES2   RELU  XSRC OUT
+        const bool up = (kind == kEpiResUpOutAct) | (kind == kEpiResUpOut);
+        if (has_res) {
+          if (x_src == 2) {
+            if (up) epi_slab<true, true, true, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);    // kEpiResUpOutAct
+            else    epi_slab<true, true, false, false, 2, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiResOutAct
+          } else if (x_src == 1) {
+            epi_slab<true, true, false, false, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h);          // kEpiResX
+          } else {
+            if (up) epi_slab<true, true, true, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);    // kEpiResUpOut
+            else    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiResOut
+          }
+        } else {
+          if (x_src) epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluX
+          else       epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiReluOut
         }
         if (has_res && st.out) {
           // in-place output: this warp's 32 rows of the slab go out as one TMA store; the slab is handed back
@@ -794,21 +813,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     };
 
     int x0 = 0, y0 = 0, n0 = 0;
+    TilePix tp_cur = tile_pix(0, 0, 0), tp_next = tp_cur;
     for (int t = -1, pt = pt0 - pstride;; ++t, pt += pstride) {
       const bool has_next = pt + pstride < n_pt;
       int nx0 = 0, ny0 = 0, nn0 = 0;
-      if (has_next) decode_tile(2 * (pt + pstride) + (int)rank, nx0, ny0, nn0);
+      if (has_next) {
+        decode_tile(2 * (pt + pstride) + (int)rank, nx0, ny0, nn0);
+        tp_next = tile_pix(nx0, ny0, nn0);
+      }
 #pragma unroll 1
       for (int sidx = 0; sidx < n_chain; ++sidx) {
         const bool head_step = (n_chain == 1) || (sidx == head_after);
         if (head_step ? !has_next : (t < 0)) continue;
         const int i = head_step ? 0 : (sidx < head_after ? sidx + 1 : sidx);
-        run_stage(i, head_step ? t + 1 : t, head_step ? nx0 : x0, head_step ? ny0 : y0, head_step ? nn0 : n0);
+        run_stage(i, head_step ? t + 1 : t, head_step ? nx0 : x0, head_step ? ny0 : y0, head_step ? nn0 : n0,
+                  head_step ? tp_next : tp_cur);
       }
       if (!has_next) break;
       x0 = nx0;
       y0 = ny0;
       n0 = nn0;
+      tp_cur = tp_next;
     }
     if (lane == 0) tma_store_wait_all();  // every output tile has left shared memory and is written
   }
