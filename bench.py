@@ -244,18 +244,40 @@ def run_b200(args):
     host_images.copy_(images)
     host_x3d = torch.empty((T * world, 38, 3), dtype=torch.float64).pin_memory()
     host_cam = torch.empty((CAMS, 6), dtype=torch.float64).pin_memory()
-    stage = torch.empty_like(images)
+    # e2e: two device staging buffers and a copy stream -- the host->device copy of step k+1 runs while step k
+    # computes (every timed step still issues exactly one copy of a full step's inputs inside the timed region)
+    stages = [torch.empty_like(images), torch.empty_like(images)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"k": 0, "primed": False}
+
+    def h2d(slot):
+        copy_stream.wait_event(consumed[slot])          # the step that last read this buffer is done with it
+        with torch.cuda.stream(copy_stream):
+            stages[slot].copy_(host_images, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def step_resident():
         out = pipe.run(images, T, group=group)
         return gather_frames(out["points3d_wo_procrustes"], group), out
 
     def step_e2e():
-        stage.copy_(host_images, non_blocking=True)                                  # H2D inside the timed region
-        out = pipe.run(stage, T, group=group)
+        cur = e2e_state["k"] & 1
+        main = torch.cuda.current_stream()
+        if not e2e_state["primed"]:                                                  # very first step: its own copy
+            consumed[0].record(main)
+            consumed[1].record(main)
+            h2d(cur)
+            e2e_state["primed"] = True
+        h2d(cur ^ 1)                                                                 # H2D of the next step's inputs
+        main.wait_event(ready[cur])
+        out = pipe.run(stages[cur], T, group=group)
+        consumed[cur].record(main)
         x3d = gather_frames(out["points3d_wo_procrustes"], group)
         host_x3d.copy_(x3d, non_blocking=True)                                       # D2H of the result
         host_cam.copy_(out["cam_rt"], non_blocking=True)
+        e2e_state["k"] += 1
         return x3d, out
 
     def barrier():
