@@ -17,14 +17,18 @@
 //           warpgroups can take 200 each: the heavy epilogues spilled at the 168 registers a 384-thread
 //           block allows, and with 227 KB of shared memory (no L1) a spill reload is an L2 round trip
 //   warps 4..11  epilogue: two groups of four warps (one TMEM lane quarter each), group g takes the
-//           64-channel slabs sl = g, g+2 of every stage
+//           64-channel slabs sl = g, g+2 of every stage; inside a warp, lanes l and l+16 share two pixel
+//           rows and split their channels (see epi_slab)
 //
 // Stage i of a tile:
-//   MMA      D(acc_i) = A_i * W_i^T;  A_0 from shared memory (TMA), A_i (i >= 1) from tensor memory
-//   epilogue (each CTA for its own tile, out of its own tensor memory; "done" is counted on the leader's
-//            barrier: 8 warps of each CTA) tcgen05.ld acc_i -> scale/shift (+ residuals) -> ReLU / bf16 rounding
-//            -> optional bf16 store straight from registers (each thread owns one pixel row: 64
-//               contiguous bytes per 32 channels = two full-sector 256-bit stores)
+//   MMA      D(acc_i) = A_i * W_i^T;  A_0 from shared memory (TMA), A_i (i >= 1) from tensor memory.  The MMAs
+//            over K block k of stage i+1 wait only for slab k of stage i's epilogue (one barrier per slab),
+//            so they overlap the epilogue of the remaining slabs
+//   epilogue (each CTA for its own tile, out of its own tensor memory; arrivals are counted on the leader's
+//            barriers: 4 warps of each CTA per slab, 8 per stage) tcgen05.ld acc_i -> scale/shift
+//            (+ residuals) -> ReLU / bf16 rounding
+//            -> stored stages with a residual: bf16(v) written in place into the residual slab, which then
+//               leaves with one TMA store per warp quarter; stored stages without: 256-bit stores from registers
 //            -> optional next-BatchNorm + ReLU -> tcgen05.st of the bf16 operand of stage i+1 IN PLACE
 //               over the first half of the accumulator columns it was computed from
 // Tensor memory holds three regions, P = [0,128), Q = [128,384), R = [384,512); launch_conv_chain maps
