@@ -142,6 +142,32 @@ extern "C" int df3d_heatmap_argmax(const void* hm_dev, int dtype, int B, int K, 
   return DF3D_OK;
 }
 
+// Decode of the keys the score-head epilogue accumulates (conv_gemm.cu, ConvParams::amax_keys): key =
+// order-preserving bits of the peak << 32 | ~flat index.  Also clears the keys for the next forward.
+__global__ void argmax_keys_decode_kernel(unsigned long long* __restrict__ keys, int n, int Cpad, int K,
+                                          int32_t* __restrict__ idx, float* __restrict__ conf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * Cpad) return;
+  const int b = g / Cpad, c = g % Cpad;
+  const unsigned long long key = keys[g];
+  keys[g] = 0ull;
+  if (c >= K) return;
+  const uint32_t o = (uint32_t)(key >> 32);
+  const uint32_t bits = o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu);
+  idx[(size_t)b * K + c] = (int32_t)(0xffffffffu - (uint32_t)key);
+  conf[(size_t)b * K + c] = __uint_as_float(bits);
+}
+
+namespace df3d {
+int launch_argmax_keys_decode(unsigned long long* keys, int B, int Cpad, int K, int32_t* idx, float* conf, cudaStream_t s) {
+  if (B == 0) return DF3D_OK;
+  const int n = B * Cpad;
+  argmax_keys_decode_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, B, Cpad, K, idx, conf);
+  DF3D_LAUNCH_CHECK("argmax_keys_decode_kernel");
+  return DF3D_OK;
+}
+}  // namespace df3d
+
 extern "C" int df3d_heatmap_argmax_nhwc(const float* hm_dev, int B, int H, int W, int Cpad, int K,
                                         int32_t* idx_dev, float* conf_dev, void* stream) {
   using namespace df3d;

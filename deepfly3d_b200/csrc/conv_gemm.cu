@@ -254,25 +254,55 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 
-      if (p.out_f32) {
-        // fp32 score maps of the last stack (BN = 32): direct, predicated stores
+      if (p.out_f32 || p.amax_keys) {
+        // fp32 score maps of the last stack (BN = 32): direct, predicated stores and / or the fused arg-max
         const int x = x0 + m % p.tw, y = y0 + (m / p.tw) % p.th, n = n0 + m / (p.tw * p.th);
         uint32_t r[32];
         tmem_ld_32x32(t_row, r);
         tmem_ld_wait();
-        if (n < p.B) {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          v[c] = fmaf(__uint_as_float(r[c]), lds_f32(aff_base + 4u * (nt * BN + c)), lds_f32(aff_base + 1024u + 4u * (nt * BN + c)));
+          if (p.relu1) v[c] = fmaxf(v[c], 0.0f);
+        }
+        if (p.out_f32 && n < p.B) {
           float* o = p.out_f32 + (((size_t)n * p.H + y) * p.W + x) * p.f32_ld + nt * BN;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v[4];
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.amax_keys) {
+          // heat-map arg-max without the heat-map (reference read-out README.md:404, df2d behind core.py:177-185):
+          // per channel the warp's maximum (redux) and its lowest lane = lowest flat index inside the tile; lane c
+          // keeps channel c's key, the four warps meet in shared memory, one atomicMax per (tile, channel)
+          const uint32_t myflat = (uint32_t)(y * p.W + x);
+          unsigned long long key = 0ull;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = nt * BN + j * 4 + e;
-              v[e] = fmaf(__uint_as_float(r[j * 4 + e]), lds_f32(aff_base + 4u * c), lds_f32(aff_base + 1024u + 4u * c));
-              if (p.relu1) v[e] = fmaxf(v[e], 0.0f);
+          for (int c = 0; c < 32; ++c) {
+            if (c < p.amax_k) {  // warp-uniform
+              const uint32_t b = __float_as_uint(v[c] + 0.0f);  // -0 -> +0: equal values, first index wins
+              const uint32_t o = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);  // order-preserving
+              const uint32_t mx = __reduce_max_sync(0xffffffffu, o);
+              const uint32_t first = (uint32_t)__ffs(__ballot_sync(0xffffffffu, o == mx)) - 1u;
+              const uint32_t fl = __shfl_sync(0xffffffffu, myflat, (int)first);
+              if (lane == c) key = ((unsigned long long)mx << 32) | (unsigned long long)(0xffffffffu - fl);
             }
-            reinterpret_cast<float4*>(o)[j] = make_float4(v[0], v[1], v[2], v[3]);
           }
+          // scratch: the scale2 / shift2 quarter of the constant area (unused on this path): [group][warp][32] keys
+          const uint32_t scratch = aff_base + 2048u + (uint32_t)(grp * 4 + q) * 256u + (uint32_t)lane * 8u;
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(scratch), "l"(key) : "memory");
+          named_bar_sync(bar_a, kEpiThreads);
+          if (q == 0 && lane < p.amax_k) {
+            unsigned long long best = key;
+#pragma unroll
+            for (int w = 1; w < 4; ++w) {
+              unsigned long long k2;
+              asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k2) : "r"(scratch + (uint32_t)w * 256u));
+              best = k2 > best ? k2 : best;
+            }
+            atomicMax(p.amax_keys + (size_t)n0 * BN + lane, best);
+          }
+          named_bar_sync(bar_b, kEpiThreads);  // the scratch may be rewritten by this group's next tile
         }
       } else {
 #pragma unroll 1
@@ -459,7 +489,10 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
   DF3D_REQUIRE(p.n_tiles_n * BN <= 256, DF3D_EUNSUPPORTED, "launch_conv_gemm: more than 256 output channels");
   DF3D_REQUIRE(!(p.out_f32 && (p.out_raw || p.out_act || p.residual)), DF3D_EUNSUPPORTED,
                "launch_conv_gemm: the fp32 output path takes no residual / bf16 outputs");
-  DF3D_REQUIRE(p.out_f32 || BN >= 64, DF3D_EUNSUPPORTED, "launch_conv_gemm: bf16 outputs need BN >= 64");
+  DF3D_REQUIRE(p.out_f32 || p.amax_keys || BN >= 64, DF3D_EUNSUPPORTED, "launch_conv_gemm: bf16 outputs need BN >= 64");
+  DF3D_REQUIRE(!p.amax_keys || (BN == 32 && p.n_tiles_n == 1 && p.nb == 1 && p.amax_k >= 1 && p.amax_k <= 32 &&
+                                !(p.out_raw || p.out_act || p.residual)),
+               DF3D_EUNSUPPORTED, "launch_conv_gemm: the fused arg-max needs the fp32 path (BN = 32), one image per tile");
   // shared-memory budget -> ring depths
   const int stage_bytes = kABytes + BN * 128;
   const int fixed = 1024 + kAffBytes + kBarBytes + (p.out_raw ? 2 * kSlabBytes : 0) + (p.out_act ? 2 * kSlabBytes : 0);

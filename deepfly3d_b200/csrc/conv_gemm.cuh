@@ -38,6 +38,12 @@ struct ConvParams {
   __nv_bfloat16* out_raw;
   __nv_bfloat16* out_act;
   float* out_f32;
+  // fp32 path only (score head): arg-max fused into the epilogue -- per (image, channel) one 64-bit key
+  // (order-preserving bits of the value << 32 | ~flat pixel index), combined with atomicMax; first occurrence
+  // wins ties like the stand-alone kernel.  [B][BN] keys, zero before the launch; needs nb == 1.  May be set
+  // with or without out_f32 (the heat-map itself is only stored when the caller asks for it).
+  unsigned long long* amax_keys;
+  int amax_k;  // real channels (<= BN)
   int res_ld, raw_ld, act_ld, f32_ld;  // channel strides (elements per pixel)
   int relu1;
 };

@@ -207,6 +207,7 @@ struct df3d_hg {
   std::vector<std::vector<float>> merged_w, merged_b;  // per-stack merged fc_/score_/score weights
   uint16_t* d_w = nullptr;
   float* d_a = nullptr;
+  unsigned long long* d_keys = nullptr;  // [max_batch][kHeatPad] arg-max keys of the fused score head (zero between forwards)
   size_t ws_bytes = 0;
   int ops_per_chunk = 0;
   // plan for the workspace pointer it was built for
@@ -214,6 +215,7 @@ struct df3d_hg {
   std::vector<Op> ops;            // plan under construction / lane 0 (all lanes share its structure)
   std::vector<std::vector<Op>> lane_ops;
   char* heat_ptr = nullptr;  // fp32 score tensor of the last stack inside the workspace
+  int score_nb = 0;          // images per M tile of the score head (the fused arg-max needs 1)
   int Hh = 0, Wh = 0;
   // optional per-launch timing (bench / profiling only): events[chunk][op][2]
   bool timing = false;
@@ -222,6 +224,8 @@ struct df3d_hg {
 };
 
 namespace df3d {
+
+int launch_argmax_keys_decode(unsigned long long* keys, int B, int Cpad, int K, int32_t* idx, float* conf, cudaStream_t s);  // argmax.cu
 
 // One emission pass.  dry == true: pack weights / affines on the host and size the workspace.
 // dry == false: same traversal (identical offsets), but produce launchable ops for `base`.
@@ -785,6 +789,10 @@ struct Emitter {
         Affine as = conv_affine(s.score, nullptr, kHeatPad);
         Tensor heat = talloc(H4, W4, kHeatPad, 4);
         conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat, fpp(s.score));
+        if (!dry && !err) {  // the score head: arg-max fused into its epilogue (see forward)
+          hg->ops.back().variant = -1;
+          hg->score_nb = hg->ops.back().nb;
+        }
         tfree(f);
         if (!dry && !err) {
           Op op;
@@ -945,6 +953,10 @@ struct Emitter {
         Affine as = conv_affine(s.score, nullptr, kHeatPad);
         Tensor heat = talloc(H4, W4, kHeatPad, 4);
         conv(f, wsc, 1, kCh, kHeatPad, kHeatPad, as, false, nullptr, nullptr, nullptr, nullptr, &heat, fpp(s.score));
+        if (!dry && !err) {  // the score head: arg-max fused into its epilogue (see forward)
+          hg->ops.back().variant = -1;
+          hg->score_nb = hg->ops.back().nb;
+        }
         tfree(f);
         if (!dry && !err) {
           Op op;
@@ -1106,6 +1118,8 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&hg->join_ev[l], cudaEventDisableTiming);
   }
   if (ce == cudaSuccess) ce = cudaMalloc(&hg->d_a, hg->ablob.size() * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMalloc(&hg->d_keys, (size_t)hg->desc.max_batch * kHeatPad * sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(hg->d_keys, 0, (size_t)hg->desc.max_batch * kHeatPad * sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_w, hg->wblob.data(), hg->wblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) ce = cudaMemcpy(hg->d_a, hg->ablob.data(), hg->ablob.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
@@ -1113,6 +1127,7 @@ extern "C" int df3d_hg_create(const df3d_hg_desc* desc, const float* params_host
     (void)cudaGetLastError();
     if (hg->d_w) cudaFree(hg->d_w);
     if (hg->d_a) cudaFree(hg->d_a);
+    if (hg->d_keys) cudaFree(hg->d_keys);
     delete hg;
     return DF3D_ECUDA;
   }
@@ -1125,6 +1140,7 @@ extern "C" void df3d_hg_destroy(df3d_hg* hg) {
   if (!hg) return;
   if (hg->d_w) cudaFree(hg->d_w);
   if (hg->d_a) cudaFree(hg->d_a);
+  if (hg->d_keys) cudaFree(hg->d_keys);
   for (cudaEvent_t ev : hg->events) cudaEventDestroy(ev);
   if (hg->fork_ev) cudaEventDestroy(hg->fork_ev);
   for (int l = 1; l < 4; ++l) {
@@ -1221,7 +1237,7 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
     for (size_t oi = 0; oi < n_ops; ++oi) {
       const Op& op = ops[oi];
       if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi], ls));
-      if (op.variant != 0 && op.variant != (gray ? 2 : 1)) {  // the other stem variant
+      if (op.variant > 0 && op.variant != (gray ? 2 : 1)) {  // the other stem variant
         if (hg->timing) DF3D_CUDA(cudaEventRecord(hg->events[ev_base + 2 * oi + 1], ls));
         continue;
       }
@@ -1244,6 +1260,13 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
           ConvParams p = op.conv;
           p.B = bc;
           p.tiles_b = (bc + op.nb - 1) / op.nb;
+          if (op.variant == -1 && op.nb == 1) {
+            // score head: the arg-max is taken in the epilogue; the fp32 maps only go to HBM when
+            // the caller asked for them
+            p.amax_keys = hg->d_keys + (size_t)c0 * kHeatPad;
+            p.amax_k = K;
+            if (!heatmap_dev) p.out_f32 = nullptr;
+          }
           if (int e = launch_conv_gemm(p, op.BN, sms, ls)) return e;
           break;
         }
@@ -1261,9 +1284,14 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
             return e;
           break;
         case OP_ARGMAX:
-          if (int e = df3d_heatmap_argmax_nhwc(reinterpret_cast<const float*>(op.in0), bc, op.H, op.W, op.C, K,
-                                               idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, ls))
+          if (hg->score_nb == 1) {  // keys written by the score head's epilogue
+            if (int e = launch_argmax_keys_decode(hg->d_keys + (size_t)c0 * kHeatPad, bc, kHeatPad, K, idx_dev + (size_t)c0 * K,
+                                                  conf_dev + (size_t)c0 * K, ls))
+              return e;
+          } else if (int e = df3d_heatmap_argmax_nhwc(reinterpret_cast<const float*>(op.in0), bc, op.H, op.W, op.C, K,
+                                                      idx_dev + (size_t)c0 * K, conf_dev + (size_t)c0 * K, ls)) {
             return e;
+          }
           if (heatmap_dev)
             DF3D_CUDA(cudaMemcpyAsync(heatmap_dev + (size_t)c0 * heat_elems, op.in0, (size_t)bc * heat_elems * sizeof(float),
                                       cudaMemcpyDeviceToDevice, ls));
