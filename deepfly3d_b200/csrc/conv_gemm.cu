@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "conv_gemm.cuh"
+#include "epilogue.cuh"
 #include "sm100.cuh"
 
 namespace df3d {
@@ -234,6 +235,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       row2_off = (uint32_t)r2 * 128u;
       sw2 = (uint32_t)(r2 & 7);
     }
+    // fast path (epilogue.cuh): two pixel rows per lane -- lanes l and l + 16 share rows r16, r16 + 16 of the
+    // quarter and split a slab's 64 channels (every per-channel constant is fetched once for two rows)
+    const uint32_t hh = (uint32_t)lane >> 4;
+    uint32_t row_off2[2], sw_2[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int m2 = q * 32 + 16 * w + (lane & 15);
+      row_off2[w] = (uint32_t)m2 * 128u;
+      sw_2[w] = (uint32_t)(m2 & 7);
+    }
+    const uint8_t* const smg = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the carve-up
+    // the combinations the hourglass plans use most; anything else takes the generic loop below
+    const bool fast = has_raw && !has_res2 && !(has_res && p.relu1) && !p.out_f32;
     uint32_t it = 0, rslot = 0, rphase = 0;
     const uint32_t obuf = (uint32_t)grp;  // one staging buffer per group and output kind
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -315,6 +329,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           // the group's previous bulk store must have read the staging buffer out (a tile ago for one-slab tiles)
           if (leader) tma_store_wait_read<0>();
           named_bar_sync(bar_a, kEpiThreads);
+          if (fast) {
+            EpiRow row[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              row[w].rrow_s = res_base + rslot * res_slot_bytes + row_off2[w];
+              row[w].rrow2_s = 0;
+              row[w].sw = sw_2[w];
+              row[w].sw2 = 0;
+              row[w].out = nullptr;
+              row[w].store = false;
+              row[w].raw_s = raw_base + obuf * kSlabBytes + row_off2[w];
+              row[w].act_s = act_base + obuf * kSlabBytes + row_off2[w];
+            }
+            const int c0 = nt * BN + sl * 64 + (int)hh * 32;  // this lane's first channel
+            const float4* const c1 = reinterpret_cast<const float4*>(smg + (aff_base - smem_base)) + (c0 >> 2);
+            const float4 *h1 = c1 + 64, *c2 = c1 + 128, *h2 = c1 + 192;  // scale1 | shift1 | scale2 | shift2, 256 floats (64 float4) each
+            const uint32_t t_slab = t_row + sl * 64;
+            //                      UNIT   RES    RES2   RELU   XSRC OUT   STAGED
+            if (has_res) {
+              if (has_act) epi_slab<false, true, false, false, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+              else         epi_slab<false, true, false, false, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+            } else if (p.relu1) {
+              if (has_act) epi_slab<false, false, false, true, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+              else         epi_slab<false, false, false, true, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+            } else {
+              if (has_act) epi_slab<false, false, false, false, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+              else         epi_slab<false, false, false, false, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+            }
+          } else
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
