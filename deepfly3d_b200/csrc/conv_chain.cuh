@@ -30,7 +30,8 @@ struct ChainStage {
   const float* shift1;
   const float* scale2;
   const float* shift2;
-  __nv_bfloat16* out_raw;  // bf16 output of this stage, NHWC with `n` channels per pixel (256-bit stores), or null
+  __nv_bfloat16* out_raw;  // bf16 output of this stage, NHWC with `n` channels per pixel, or null (stored through tmOutQ
+                           // from the residual slab when the stage has a residual, else by 256-bit stores)
   int n;         // output channels: 128 or 256
   int kblocks;   // K / 64 (head: taps * Cin/64; later stages: n of the previous stage / 64)
   int relu1;

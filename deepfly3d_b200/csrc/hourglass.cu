@@ -5,11 +5,15 @@
 // df3d_hg_create parses the float32 parameter blob, folds every BatchNorm into a per-channel
 // (scale, shift) pair, packs every conv weight to bf16 [CoutPad][taps*CinPad] (K-major) and
 // uploads both once.  The forward is a fixed list of launches over a chunk of images:
-//   stem_im2col -> conv_gemm (tcgen05) x N, maxpool_bn_relu -> argmax.
+//   stem_im2col -> conv_gemm / conv_chain (tcgen05) x N, maxpool_bn_relu -> score head with the arg-max in
+//   its epilogue -> key decode.
 // Each conv's epilogue applies the *next* BatchNorm + ReLU (pre-activation bottlenecks), the
-// residual add, the hourglass' nearest x2 up-sample + add and the bf16 rounding, so a bottleneck is
-// exactly three (four with a projection) GEMM launches and no elementwise pass.  All activations live in the caller's workspace; a
-// small free-list arena reuses buffers so the working set stays small.
+// residual add, the hourglass' nearest x2 up-sample + add and the bf16 rounding.  Unfused (DF3D_HG_FUSE=0) a
+// bottleneck is three (four with a projection) GEMM launches and no elementwise pass; in the default plan
+// (DF3D_HG_FUSE=2) one conv_chain launch runs [3x3 -> conv3 (+ residual, + up-sample add) -> next block's
+// conv1], and the inter-stack chain five convs, with the intermediates kept in tensor memory.  All
+// activations live in the caller's workspace; a small free-list arena reuses buffers so the working set
+// stays small.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
