@@ -8,12 +8,14 @@ A step = one pass of the hot path over a batch of synthetic frames:
     calibrate_calc + save run in the reference, minus file I/O.
 
   value : frames/s with the images already resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public pipeline call with PINNED HOST images: H2D copy of the
-          step's images and D2H of the 3-D joints + cameras inside the timed region
-  roofline : dominant kernel = conv_gemm_kernel (tcgen05 implicit-GEMM convs), achieved =
-          algorithmic conv FLOPs of the step / summed device time of its launches (CUDA events on
-          the launching stream, taken during the timed region), peak = MEASURED_PEAKS.json
-          bf16_tflops_sustained (fallback 1400 TF/s "of fallback")
+  e2e   : same metric through the public pipeline call with PINNED HOST images: every timed step issues
+          one H2D copy of a full step's images (double-buffered on a copy stream: the copy of step k+1
+          overlaps the compute of step k) and the D2H of the 3-D joints + cameras
+  roofline : dominant kernels = conv_chain_kernel + conv_gemm_kernel (tcgen05 conv chains and implicit-GEMM
+          convs), achieved = algorithmic conv FLOPs of the step / summed device time of their launches (CUDA
+          events on the launching stream, taken during the timed region), peak = MEASURED_PEAKS.json
+          bf16_tflops_sustained (fallback 1400 TF/s "of fallback"); traffic = DRAM bytes per conv launch
+          from the committed ncu metrics pass (profiles/conv_gemm_traffic.json)
   cpu_baseline : the CPU oracle (PyTorch fp32 hourglass + numpy DLT + SciPy BA, all host threads)
           on a bounded sample
 
