@@ -36,6 +36,10 @@ SIGNATURES = {
     "df3d_heatmap_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "df3d_heatmap_argmax_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "df3d_resize_gray_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "df3d_jpeg_create": (_i, [C.POINTER(_vp)]),
+    "df3d_jpeg_destroy": (None, [_vp]),
+    "df3d_jpeg_info": (_i, [_vp, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "df3d_jpeg_decode_gray": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "df3d_pack_points2d": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), _i, _i, _vp, _vp, _vp]),
     "df3d_triangulate_dlt": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "df3d_projection_matrices": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

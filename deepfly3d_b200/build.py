@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             if f.read().strip() == fp:
                 return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-ldl"]  # dlopen: nvJPEG is bound at run time (jpeg.cu)
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

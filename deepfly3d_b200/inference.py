@@ -7,9 +7,10 @@
                             network frame
     conf     (7, T, 19, 1)  float32 peak value
 
-Image ingest: the JPEG files are decoded on the host (the reference's path too; SURVEY.md section 8(f)
-row 1); the resize to the network input runs on the device (csrc/ingest.cu, bit-identical to the
-cv2.resize(..., INTER_LINEAR) the loader used to do on the host).
+Image ingest: by default the JPEG files are decoded on the host (the
+reference's path too, bit-identical frames); `gpu_decode=True` decodes them with nvJPEG on the device (a few
+grey levels away).  The resize to the network input always runs on the device (csrc/ingest.cu, bit-identical
+to the cv2.resize(..., INTER_LINEAR) the loader used to do on the host).
 """
 import os
 
@@ -52,13 +53,39 @@ def read_images(folder, max_img_id, pin_memory=True):
     return out
 
 
-def load_images(folder, max_img_id, size_hw, pin_memory=True, device="cuda"):
+_JPEG = {}
+
+
+def decode_images_device(folder, max_img_id, device="cuda"):
+    """-> uint8 tensor (7*T, Hs, Ws) ON THE DEVICE: the compressed files are read on the host and decoded by
+    nvJPEG (ops.JpegDecoder).  Opt-in: a few grey levels away from the host's libjpeg read."""
+    from . import ops
+
+    dec = _JPEG.get("dec")
+    if dec is None:
+        dec = _JPEG["dec"] = ops.JpegDecoder()
+    streams = []
+    for c in range(NUM_CAMERAS):
+        for t in range(max_img_id + 1):
+            path = image_name(folder, c, t)
+            if not os.path.isfile(path):
+                raise FileNotFoundError(f"cannot read {path}")
+            with open(path, "rb") as f:
+                streams.append(f.read())
+    return dec.decode_gray(streams, device=device)
+
+
+def load_images(folder, max_img_id, size_hw, pin_memory=True, device="cuda", gpu_decode=False):
     """-> uint8 tensor (7*T, H, W) gray ON THE DEVICE, resized to the network input (camera-major)."""
     from . import ops
 
-    native = read_images(folder, max_img_id, pin_memory=pin_memory)
-    C, T, Hs, Ws = native.shape
-    dev = native.reshape(C * T, Hs, Ws).to(device, non_blocking=True)
+    if gpu_decode:
+        dev = decode_images_device(folder, max_img_id, device=device)
+        Hs, Ws = dev.shape[1:]
+    else:
+        native = read_images(folder, max_img_id, pin_memory=pin_memory)
+        C, T, Hs, Ws = native.shape
+        dev = native.reshape(C * T, Hs, Ws).to(device, non_blocking=True)
     if (Hs, Ws) != tuple(size_hw):
         dev = ops.resize_gray_u8(dev, size_hw)
     return dev
@@ -125,14 +152,15 @@ def get_engine(state_dict, in_h, in_w, max_batch, device="cuda"):
 
 def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return_confidence=True, max_img_id=None,
                      batch_size=8, disable_pin_memory=False, state_dict=None, weights=None, input_size=None,
-                     device="cuda"):
+                     device="cuda", gpu_decode=False):
     """Runs the hourglass on every camera_{0..6}_img_{0..max_img_id}.jpg of `folder`."""
     if max_img_id is None:
         raise ValueError("max_img_id is required")
     Hh, Wh = HEATMAP_SHAPE
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
-    dev_images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory, device=device)
+    dev_images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory, device=device,
+                             gpu_decode=gpu_decode)
     sd = state_dict if state_dict is not None else load_state_dict(weights)
     # batch_size is the reference's DataLoader batch; here the whole folder is one device batch and
     # the engine chunks internally, so it only bounds the workspace for tiny folders

@@ -65,6 +65,47 @@ def resize_gray_u8(images, size_hw):
     return out
 
 
+class JpegDecoder:
+    """Device-side JPEG decode (luminance) through nvJPEG, bound at run time.  Opt-in: a few grey levels away
+    from the host's libjpeg read, see include/df3d_b200.h."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib.df3d_jpeg_create(C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.df3d_jpeg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def image_size(self, data):
+        """-> (H, W) of a compressed stream (bytes)."""
+        w, h = C.c_int(), C.c_int()
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        check(lib.df3d_jpeg_info(self._h, buf, len(data), C.byref(w), C.byref(h)))
+        return h.value, w.value
+
+    def decode_gray(self, streams, device="cuda"):
+        """streams: list of bytes, all of one size -> (n, H, W) uint8 tensor on the device."""
+        n = len(streams)
+        if n == 0:
+            return torch.empty((0, 0, 0), dtype=torch.uint8, device=device)
+        H, W = self.image_size(streams[0])
+        out = torch.empty((n, H, W), dtype=torch.uint8, device=device)
+        bufs = [(C.c_ubyte * len(s)).from_buffer_copy(s) for s in streams]
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * n)(*[len(s) for s in streams])
+        with torch.cuda.device(out.device):
+            check(lib.df3d_jpeg_decode_gray(self._h, ptrs, lens, n, _ptr(out), H, W, _stream()))
+        return out
+
+
 def pack_points2d(idx, C_, T, heatmap_shape, camera_ordering, image_shape):
     """idx (C*T,K) int32 (camera-major) -> points2d (C,T,2K,2) f64 normalised (row,col),
     pts_xy (C,T,2K,2) f64 pixel (x,y).  image_shape = [W, H] like Core.image_shape."""

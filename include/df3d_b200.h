@@ -72,6 +72,21 @@ int df3d_resize_gray_u8(const uint8_t* src_dev, int B, int Hs, int Ws, uint8_t* 
                         void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * JPEG decode on the device (luminance), bound to nvJPEG at run time (dlopen; the library itself does not
+ * depend on it).  Opt-in alternative to reading camera_C_img_I.jpg on the host (the reference's path behind
+ * df2d.inference.inference_folder, df3d/core.py:177-185; frames come from core.py:446-459).  nvJPEG's inverse
+ * DCT differs from libjpeg's by a few grey levels, so results are NOT bit-identical to the host read.
+ *
+ *   data, lens : HOST arrays of n compressed streams        dst_dev : (n, H, W) uint8 on the device
+ * ------------------------------------------------------------------------------------------ */
+typedef struct df3d_jpeg df3d_jpeg;
+int df3d_jpeg_create(df3d_jpeg** out);
+void df3d_jpeg_destroy(df3d_jpeg* j);
+int df3d_jpeg_info(df3d_jpeg* j, const uint8_t* data, size_t len, int* width, int* height);
+int df3d_jpeg_decode_gray(df3d_jpeg* j, const uint8_t* const* data, const size_t* lens, int n, uint8_t* dst_dev,
+                          int H, int W, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * 19 -> 38 joint packing.  Replaces df3d/core.py:187-203 (Core.pose2d_estimation after
  * inference_folder) and the pixel scaling of core.py:247 (`points2d * image_shape[::-1]`).
  *
