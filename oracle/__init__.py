@@ -15,6 +15,9 @@ The oracle therefore restates their observable behaviour:
   ``tests/data/reference_df3d/df3d_result_3d.pkl`` from ``df3d_result_2d.pkl``
   + ``data/calib.pkl`` at the tolerances of the reference's ``test_calibration``
   (``tests/test_df3d.py:198-244``); see ``tests/test_oracle_golden.py``.
+* image ingest (``oracle.ingest``): the loader's resize, **pinned** bit for bit against
+  ``cv2.resize(..., INTER_LINEAR)`` itself (``tests/test_oracle_ingest.py``) -- the definition
+  this port's host loader has always used; df2d's own resize mode is not verifiable offline.
 * 2-D half (``oracle.hourglass``, ``oracle.argmax``): **parity unpinned** -- the
   golden 2-D points need the pretrained ``sh8_deepfly.tar`` weights that df2d
   downloads at run time (reference ``df3d/config.py:30-32``); they are not in
