@@ -12,12 +12,12 @@ DF3D_MAX_CAMS = 8
 
 
 class BAOpts(C.Structure):
-    _fields_ = [("max_iters", C.c_int), ("ftol", C.c_double), ("lambda0", C.c_double)]
+    _fields_ = [("max_iters", C.c_int), ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double)]
 
 
 class BAReport(C.Structure):
     _fields_ = [
-        ("cost0", C.c_double), ("cost", C.c_double), ("lambda_", C.c_double),
+        ("cost0", C.c_double), ("cost", C.c_double), ("reg", C.c_double),
         ("iters", C.c_int32), ("accepted", C.c_int32), ("n_obs", C.c_int32), ("status", C.c_int32),
     ]
 
@@ -45,13 +45,7 @@ SIGNATURES = {
     "df3d_projection_matrices": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "df3d_bundle_adjust_workspace_bytes": (_sz, [_i, _i, _i]),
     "df3d_bundle_adjust": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(BAOpts), _vp, _vp, _vp, _sz, _vp]),
-    "df3d_ba_system_doubles": (_sz, [_i]),
-    "df3d_ba_begin": (_i, [_vp, C.POINTER(BAOpts), _i, _i, _i, _vp, _sz, _vp]),
-    "df3d_ba_linearize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    "df3d_ba_solve": (_i, [_i, _vp, _vp, _vp]),
-    "df3d_ba_evaluate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    "df3d_ba_decide": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
-    "df3d_ba_end": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "df3d_bundle_adjust_launches": (_i, [C.POINTER(BAOpts)]),
     "df3d_reprojection_error": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "df3d_hg_param_count": (_sz, [C.POINTER(HGDesc)]),
     "df3d_hg_workspace_bytes": (_sz, [C.POINTER(HGDesc)]),

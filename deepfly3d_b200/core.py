@@ -74,7 +74,11 @@ class Core:
     """Main interface to the 2d and 3d pose estimation (reference df3d/core.py:62)."""
 
     def __init__(self, input_folder: str, output_folder: Optional[str] = None, num_images_max: Optional[int] = None,
-                 camera_ordering: List[int] = [0, 1, 2, 3, 4, 5, 6], state_dict=None, weights=None):
+                 camera_ordering: List[int] = [0, 1, 2, 3, 4, 5, 6], state_dict=None, weights=None, mean=None,
+                 gpu_decode=False):
+        """Same four arguments as the reference.  Extra keywords (the reference reads them from its config,
+        df3d/config.py:30-39): `weights` = hourglass checkpoint (sh8_deepfly.tar layout) or `state_dict`,
+        `mean` = per-channel mean or the path of a mean.pth.tar, `gpu_decode` = nvJPEG instead of libjpeg."""
         self.input_folder = input_folder
         self.output_folder = self.input_folder + "_df3d" if output_folder is None else output_folder
         self.expand_videos()
@@ -93,7 +97,8 @@ class Core:
             raise ValueError(f"Image shape not specified and could not be read from {image0}")
         self.image_shape = shape                       # [W, H], e.g. [960, 480]
         self.camera_ordering = self.setup_camera_ordering(camera_ordering)
-        self._state_dict, self._weights = state_dict, weights
+        self._state_dict, self._weights, self._mean, self._gpu_decode = state_dict, weights, mean, gpu_decode
+        self.ingest_stats = {}
 
         self.camNet = None
         self.points2d = None
@@ -161,7 +166,8 @@ class Core:
         p19, conf = inference_folder(
             folder=self.input_folder, camera_ids_to_flip=flip, return_heatmap=False, return_confidence=True,
             max_img_id=self.max_img_id, batch_size=batch_size, disable_pin_memory=disable_pin_memory,
-            state_dict=self._state_dict, weights=self._weights)
+            state_dict=self._state_dict, weights=self._weights, mean=self._mean, gpu_decode=self._gpu_decode,
+            stats=self.ingest_stats)
         self.conf = conf
         # packing runs on the device from the integer arg-max indices (bit-exact with core.py:187-203)
         Hh, Wh = HEATMAP_SHAPE

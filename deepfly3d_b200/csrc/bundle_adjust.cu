@@ -1,26 +1,32 @@
 // Bundle adjustment of C camera extrinsics + all 3-D points (fp64, everything on the device).
 // Replaces pyba CameraNetwork.bundle_adjust(update_intrinsic=False, update_distort=False)
-// (reference call site df3d/core.py:249; recipe reconstructed in SURVEY.md Appendix B).
+// (reference call site df3d/core.py:249; recipe reconstructed in SURVEY.md Appendix B): pyba hands the
+// problem to scipy.optimize.least_squares(method='trf', x_scale='jac', ftol=1e-4, tr_solver='lsmr').
 //
-// Levenberg-Marquardt in the column-norm (Jacobi) scaled space SciPy's x_scale='jac' uses, with a
-// small constant damping, solved through the Schur complement on the 6C camera unknowns:
+// The bundle-adjustment gauge is free (no camera is held fixed), so WHERE the solver ends up depends on
+// its step rule; this file therefore follows SciPy's trust-region-reflective iteration for unbounded
+// problems (scipy/optimize/_lsq/trf.py::trf_no_bounds, the tr_solver == 'lsmr' branch) statement by
+// statement, with one substitution: the regularised Gauss-Newton step that SciPy gets from LSMR,
+//     gn_h = argmin |J_h p - f|^2 + reg |p|^2 ,   J_h = J diag(1 / column norm),
+// is solved exactly through the Schur complement on the 6C camera unknowns.  Measured on the CPU
+// prototype (tools/ba_proto.py): 1-2e-5 mm from SciPy at T = 15 ... 1000 frames -- the distance between
+// SciPy with its default LSMR tolerance and SciPy with a converged LSMR.
 //
-//   ba_linearize : one thread per 3-D point.  Analytic Jacobian (Rodrigues + pin-hole), per-point
-//                  V (3x3), g_p, per-observation W (6x3); contributions to U_c, g_c and to the
-//                  reduced system  S~ = sum_j W_j M_j W_j^T,  b~ = sum_j W_j M_j g_pj  with
-//                  M_j = D_p (D_p V_j D_p + lambda I)^-1 D_p  are reduced across the warp with
-//                  shuffles, accumulated in per-warp shared-memory tiles (single writer, no
-//                  atomics -> bitwise reproducible), summed per block, and the last block to finish
-//                  adds the per-block partials in a fixed order.
-//   ba_solve     : one CTA.  Camera scaling D_c from diag(U), forms
-//                  D_c (U - S~) D_c + lambda I, Cholesky, candidate cameras.
-//   ba_evaluate  : one thread per point.  Back-substitution for the point step and the candidate
-//                  cost; same last-block reduction.
-//   ba_decide    : accept / reject, lambda update, ftol test (dF < ftol * F like SciPy's TRF).
-//
-// The state lives in the caller's workspace, so a whole solve is a fixed sequence of launches
-// with no host synchronisation; the `sys` and `cost` buffers are the only data a frame-sharded
-// multi-GPU run has to all-reduce (see include/df3d_b200.h).
+// One outer iteration = a fixed sequence of launches, no host synchronisation (device-side flags turn the
+// kernels into no-ops once the solver has terminated, and skip the linearisation after a rejected step):
+//   ba_gradient : one thread per 3-D point.  Analytic Jacobian (Rodrigues + pin-hole); gradient, column
+//                 norms (Jacobi scaling, running maximum like compute_jac_scale), cost, and the pieces of
+//                 |J_h g_h|^2; the last block derives the Cauchy-step regularisation `reg`
+//   ba_schur    : one thread per point.  Per-point M = D_p (D_p V D_p + reg I)^-1 D_p; reduced system
+//                 S~ = sum W M W^T,  b~ = sum W M g_p  (warp shuffles -> per-warp shared-memory tiles with a
+//                 single writer -> per-block partials -> fixed-order sum by the last block: bit-reproducible)
+//   ba_solve    : one CTA.  D_c (U - S~) D_c + reg I, Cholesky + one refinement step -> camera part of gn_h
+//   ba_backsub  : one thread per point.  Point part of gn_h, the Gram quantities of span{g_h, gn_h}; the last
+//                 block builds the 2-D sub-problem and solves it inside the trust region
+//   ba_step     : one thread per point.  Candidate x + D step_h, its cost; the last block runs SciPy's
+//                 ratio test, radius update and termination rule, and re-solves the 2-D problem after a
+//                 rejected step
+//   ba_apply    : copies the candidate points after an accepted step
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -29,14 +35,27 @@ namespace df3d {
 constexpr int kBAThreads = 128;
 constexpr int kBAWarps = kBAThreads / 32;
 constexpr int kBAMaxBlocks = 148;
+constexpr int kMaxN = 6 * DF3D_MAX_CAMS;
 
 struct BAState {
-  double lambda, F, F0, ftol;
-  int iter, accepted, max_iters, done, status, n_obs, accept_flag, pad;
+  double Delta, F, F0, ftol, xtol, gtol, reg;
+  double gg, JgJg;        // |g_h|^2, |J_h g_h|^2
+  double T00, T10, T11;   // orthonormal basis of span{g_h, gn_h}: q1 = T00 g_h, q2 = T10 g_h + T11 gn_h
+  double B00, B01, B11;   // J_h restricted to that basis, squared
+  double gS0, gS1;        // gradient in that basis
+  double coef_g, coef_gn; // step_h = coef_g g_h + coef_gn gn_h
+  double pred, sh_norm;   // predicted reduction and |step_h| of the current candidate
+  int iter, accepted, max_iters, done, status, n_obs, accept_flag, need_lin, first, pad;
 };
 
+// ba_gradient's reduction vector
+__host__ __device__ inline int g_doubles(int C) { return 36 * C + 6 * C + 6 * C + 6; }
+__host__ __device__ inline int g_off_U(int) { return 0; }
+__host__ __device__ inline int g_off_gc(int C) { return 36 * C; }
+__host__ __device__ inline int g_off_w(int C) { return 42 * C; }
+__host__ __device__ inline int g_off_sc(int C) { return 48 * C; }  // cost, n_obs, b^T V b, |g_h points|^2, sum (x sinv)^2, [max] |g|_inf
+// ba_schur's reduction vector
 __host__ __device__ inline int sys_doubles(int C) { return 36 * C + 6 * C + 36 * C * C + 6 * C + 2; }
-// offsets inside `sys`
 __host__ __device__ inline int off_U(int) { return 0; }
 __host__ __device__ inline int off_gc(int C) { return 36 * C; }
 __host__ __device__ inline int off_S(int C) { return 42 * C; }
@@ -45,17 +64,20 @@ __host__ __device__ inline int off_cost(int C) { return 48 * C + 36 * C * C; }
 
 struct BAWorkspace {  // carved out of the caller's buffer
   BAState* state;
-  unsigned int* counters;  // [0] linearize ticket, [1] evaluate ticket
-  double* cam;             // C*6 current
-  double* cam_new;         // C*6 candidate
-  double* dcam;            // C*6 unscaled camera step
-  double* sinv_c;          // C*6 running max of camera column norms
-  double* sinv_p;          // TJ*3 running max of point column norms
+  unsigned int* counters;  // last-block tickets, one per reducing kernel
+  double* cam;             // C*6 current cameras
+  double* sinv_c;          // C*6 camera column norms (running maximum)
+  double* gc;              // C*6 camera gradient
+  double* ac;              // C*6 gc / sinv^2  (camera part of D g_h)
+  double* ghc;             // C*6 gc / sinv    (camera part of g_h)
+  double* gnc;             // C*6 camera part of gn_h
+  double* dcn;             // C*6 gnc / sinv   (camera part of D gn_h)
+  double* sinv_p;          // TJ*3 point column norms (running maximum)
+  double* gp;              // TJ*3 point gradient
+  double* gnp;             // TJ*3 point part of gn_h
   double* X_new;           // TJ*3 candidate points
-  double* partials;        // kBAMaxBlocks * sys_doubles(C)
-  double* cost_partials;   // kBAMaxBlocks * 2
-  double* sys_local;       // sys_doubles(C): used by the single-GPU driver
-  double* cost_local;      // 2
+  double* partials;        // kBAMaxBlocks * max(sys_doubles, g_doubles)
+  double* red;             // reduced vector of the last reducing kernel
 };
 
 static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* ws) {
@@ -66,19 +88,23 @@ static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* 
     return base ? base + o : nullptr;
   };
   const size_t TJ = (size_t)T * J;
+  const size_t nred = (size_t)(sys_doubles(C) > g_doubles(C) ? sys_doubles(C) : g_doubles(C));
   BAWorkspace w;
   w.state = reinterpret_cast<BAState*>(take(sizeof(BAState)));
-  w.counters = reinterpret_cast<unsigned int*>(take(4 * sizeof(unsigned int)));
+  w.counters = reinterpret_cast<unsigned int*>(take(8 * sizeof(unsigned int)));
   w.cam = reinterpret_cast<double*>(take(C * 6 * 8));
-  w.cam_new = reinterpret_cast<double*>(take(C * 6 * 8));
-  w.dcam = reinterpret_cast<double*>(take(C * 6 * 8));
   w.sinv_c = reinterpret_cast<double*>(take(C * 6 * 8));
+  w.gc = reinterpret_cast<double*>(take(C * 6 * 8));
+  w.ac = reinterpret_cast<double*>(take(C * 6 * 8));
+  w.ghc = reinterpret_cast<double*>(take(C * 6 * 8));
+  w.gnc = reinterpret_cast<double*>(take(C * 6 * 8));
+  w.dcn = reinterpret_cast<double*>(take(C * 6 * 8));
   w.sinv_p = reinterpret_cast<double*>(take(TJ * 3 * 8));
+  w.gp = reinterpret_cast<double*>(take(TJ * 3 * 8));
+  w.gnp = reinterpret_cast<double*>(take(TJ * 3 * 8));
   w.X_new = reinterpret_cast<double*>(take(TJ * 3 * 8));
-  w.partials = reinterpret_cast<double*>(take((size_t)kBAMaxBlocks * sys_doubles(C) * 8));
-  w.cost_partials = reinterpret_cast<double*>(take((size_t)kBAMaxBlocks * 2 * 8));
-  w.sys_local = reinterpret_cast<double*>(take((size_t)sys_doubles(C) * 8));
-  w.cost_local = reinterpret_cast<double*>(take(2 * 8));
+  w.partials = reinterpret_cast<double*>(take((size_t)kBAMaxBlocks * nred * 8));
+  w.red = reinterpret_cast<double*>(take(nred * 8));
   if (ws) *ws = w;
   return off;
 }
@@ -89,53 +115,55 @@ static int ba_grid(int TJ) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void ba_begin_kernel(const double* __restrict__ cam_rt, int C, int TJ, df3d_ba_opts opts, BAWorkspace ws) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void ba_begin_kernel(const double* __restrict__ cam_rt, int C, df3d_ba_opts opts, BAWorkspace ws) {
+  const int g = threadIdx.x;
   if (g == 0) {
     BAState s;
-    s.lambda = opts.lambda0;
-    s.F = -1.0;
-    s.F0 = -1.0;
+    memset(&s, 0, sizeof(s));
+    s.F = s.F0 = -1.0;
     s.ftol = opts.ftol;
-    s.iter = 0;
-    s.accepted = 0;
+    s.xtol = opts.xtol;
+    s.gtol = opts.gtol;
     s.max_iters = opts.max_iters;
-    s.done = 0;
-    s.status = 0;
-    s.n_obs = 0;
-    s.accept_flag = 0;
-    s.pad = 0;
+    s.need_lin = 1;
+    s.first = 1;
     *ws.state = s;
-    ws.counters[0] = ws.counters[1] = ws.counters[2] = ws.counters[3] = 0u;
+    for (int i = 0; i < 8; ++i) ws.counters[i] = 0u;
   }
-  if (g < C * 6) {
-    ws.cam[g] = cam_rt[g];
-    ws.cam_new[g] = cam_rt[g];
-    ws.dcam[g] = 0.0;
-    ws.sinv_c[g] = 0.0;
-  }
-  for (int i = g; i < TJ * 3; i += gridDim.x * blockDim.x) ws.sinv_p[i] = 0.0;
+  if (g < C * 6) ws.cam[g] = cam_rt[g];
 }
 
-// 3x3 symmetric positive definite inverse (adjugate); returns false if not invertible
-__device__ __forceinline__ bool inv3_sym(const double (&A)[3][3], double (&Ai)[3][3]) {
-  const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-  const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
-  const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-  const double det = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
-  if (!(fabs(det) > 0.0)) return false;
-  const double id = 1.0 / det;
-  Ai[0][0] = c00 * id;
-  Ai[0][1] = Ai[1][0] = c01 * id;
-  Ai[0][2] = Ai[2][0] = c02 * id;
-  Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
-  Ai[1][2] = Ai[2][1] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
-  Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
+// 3x3 symmetric positive definite inverse through its Cholesky factor (backward stable for the
+// ill-conditioned per-point blocks: two views of a 16 000 px lens barely constrain the depth)
+__device__ __forceinline__ bool inv3_spd(const double (&A)[3][3], double (&Ai)[3][3]) {
+  if (!(A[0][0] > 0.0)) return false;
+  const double l00 = sqrt(A[0][0]);
+  const double l10 = A[1][0] / l00, l20 = A[2][0] / l00;
+  const double d1 = A[1][1] - l10 * l10;
+  if (!(d1 > 0.0)) return false;
+  const double l11 = sqrt(d1);
+  const double l21 = (A[2][1] - l20 * l10) / l11;
+  const double d2 = A[2][2] - l20 * l20 - l21 * l21;
+  if (!(d2 > 0.0)) return false;
+  const double l22 = sqrt(d2);
+  // Li = L^-1 (lower), A^-1 = Li^T Li
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  Ai[0][0] = i00 * i00 + i10 * i10 + i20 * i20;
+  Ai[0][1] = Ai[1][0] = i10 * i11 + i20 * i21;
+  Ai[0][2] = Ai[2][0] = i20 * i22;
+  Ai[1][1] = i11 * i11 + i21 * i21;
+  Ai[1][2] = Ai[2][1] = i21 * i22;
+  Ai[2][2] = i22 * i22;
   return true;
 }
 
-// Last-block-done reduction of per-block partial vectors of length n (fixed summation order).
-__device__ __forceinline__ void reduce_partials_last_block(const double* partials, int n, double* out,
+// Last-block-done reduction of per-block partial vectors: entries [0, n_sum) are summed, [n_sum, n) take the
+// maximum, both in a fixed block order.  Returns true in every thread of the last block, after `out` is
+// complete and visible to it.
+__device__ __forceinline__ bool reduce_partials_last_block(const double* partials, int n_sum, int n, double* out,
                                                            unsigned int* ticket) {
   __shared__ bool s_last;
   __threadfence();
@@ -145,41 +173,132 @@ __device__ __forceinline__ void reduce_partials_last_block(const double* partial
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      double acc = 0.0;
+  if (!s_last) return false;
+  __threadfence();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    double acc = e < n_sum ? 0.0 : -1.0;
+    if (e < n_sum) {
       for (unsigned b = 0; b < gridDim.x; ++b) acc += partials[(size_t)b * n + e];
-      out[e] = acc;
+    } else {
+      for (unsigned b = 0; b < gridDim.x; ++b) acc = fmax(acc, partials[(size_t)b * n + e]);
     }
-    if (threadIdx.x == 0) *ticket = 0u;
+    out[e] = acc;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence();
+  __syncthreads();
+  return true;
+}
+
+// block partial = fixed-order sum (or max) of the per-warp tiles
+__device__ __forceinline__ void block_partial(const double* s_tiles, int n_sum, int n, double* part) {
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += kBAThreads) {
+    double acc = s_tiles[e];
+#pragma unroll
+    for (int w = 1; w < kBAWarps; ++w) acc = e < n_sum ? acc + s_tiles[w * n + e] : fmax(acc, s_tiles[w * n + e]);
+    part[e] = acc;
   }
 }
 
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// SciPy solve_trust_region_2d: min 0.5 p^T B p + g^T p subject to |p| <= Delta.  Same minimiser; found through the
+// eigen-decomposition of B and bisection on the secular equation instead of the roots of a quartic.
+__device__ void solve_tr_2d(double b00, double b01, double b11, double g0, double g1, double Delta, double (&p)[2]) {
+  // eigenvalues w0 <= w1, eigenvectors as a rotation (c, s)
+  const double tr = 0.5 * (b00 + b11), df = 0.5 * (b00 - b11);
+  const double rad = sqrt(df * df + b01 * b01);
+  const double w0 = tr - rad, w1 = tr + rad;
+  double vx, vy;  // eigenvector of w1
+  if (rad == 0.0) {
+    vx = 1.0;
+    vy = 0.0;
+  } else if (df >= 0.0) {
+    vx = df + rad;
+    vy = b01;
+  } else {
+    vx = b01;
+    vy = rad - df;
+  }
+  const double vn = sqrt(vx * vx + vy * vy);
+  vx /= vn;
+  vy /= vn;
+  // q1 = (vx, vy) for w1, q0 = (-vy, vx) for w0
+  const double gq0 = -vy * g0 + vx * g1, gq1 = vx * g0 + vy * g1;
+  double y0, y1;
+  bool inside = false;
+  if (w0 > 0.0) {
+    y0 = -gq0 / w0;
+    y1 = -gq1 / w1;
+    inside = (y0 * y0 + y1 * y1) <= Delta * Delta;
+  }
+  if (!inside) {
+    const double lo0 = fmax(0.0, -w0);
+    auto f = [&](double mu) {
+      const double a = gq0 / (w0 + mu), b = gq1 / (w1 + mu);
+      return sqrt(a * a + b * b) - Delta;
+    };
+    double lo = lo0, hi = lo0 + fmax(1.0, fabs(w1));
+    int guard = 0;
+    while (f(hi) > 0.0 && guard++ < 2000) hi = lo0 + 2.0 * (hi - lo0);
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (f(mid) > 0.0)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const double mu = 0.5 * (lo + hi);
+    y0 = -gq0 / (w0 + mu);
+    y1 = -gq1 / (w1 + mu);
+  }
+  p[0] = -vy * y0 + vx * y1;
+  p[1] = vx * y0 + vy * y1;
+}
+
+// candidate step inside the current trust region (thread 0 of a last block)
+__device__ void solve_subproblem(BAState* st) {
+  double p[2] = {0.0, 0.0};
+  if (st->T11 == 0.0) {  // gn_h parallel to g_h: one dimension
+    if (st->B00 > 0.0) p[0] = -st->gS0 / st->B00;
+    if (!(st->B00 > 0.0) || fabs(p[0]) > st->Delta) p[0] = st->gS0 > 0.0 ? -st->Delta : st->Delta;
+  } else {
+    solve_tr_2d(st->B00, st->B01, st->B11, st->gS0, st->gS1, st->Delta, p);
+  }
+  st->coef_g = p[0] * st->T00 + p[1] * st->T10;
+  st->coef_gn = p[1] * st->T11;
+  st->pred = -(0.5 * (p[0] * (st->B00 * p[0] + st->B01 * p[1]) + p[1] * (st->B01 * p[0] + st->B11 * p[1])) +
+               st->gS0 * p[0] + st->gS1 * p[1]);
+  st->sh_norm = sqrt(p[0] * p[0] + p[1] * p[1]);
+}
+
 // ---------------------------------------------------------------------------------------------
-// dynamic shared memory: cams [C*kCamStride] | per-warp system tiles [kBAWarps * nsys]
+// dynamic shared memory: cams [C*kCamStride] | per-warp tiles [kBAWarps * g_doubles(C)]
 __global__ void __launch_bounds__(kBAThreads)
-ba_linearize_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
-                    const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws, double* __restrict__ sys_out) {
+ba_gradient_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
+                   const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws) {
   extern __shared__ double smem[];
-  if (ws.state->done) return;
-  const double lambda = ws.state->lambda;
-  const int nsys = sys_doubles(C);
-  const int n6 = 6 * C;
+  BAState* st = ws.state;
+  if (st->done || !st->need_lin) return;
+  const bool first = st->first != 0;
+  const int n = g_doubles(C), n_sum = n - 1;
   double* s_cam = smem;
-  double* s_sys = smem + C * kCamStride;
+  double* s_t = smem + C * kCamStride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* my = s_sys + warp * nsys;  // this warp's accumulator tile
+  double* my = s_t + warp * n;
 
   if (threadIdx.x < C) stage_camera(ws.cam + threadIdx.x * 6, intr + threadIdx.x * 4, s_cam + threadIdx.x * kCamStride);
-  for (int e = threadIdx.x; e < kBAWarps * nsys; e += kBAThreads) s_sys[e] = 0.0;
+  for (int e = threadIdx.x; e < kBAWarps * n; e += kBAThreads) s_t[e] = 0.0;
   __syncthreads();
-
-  double* aU = my + off_U(C);
-  double* agc = my + off_gc(C);
-  double* aS = my + off_S(C);
-  double* ab = my + off_b(C);
-  double* acost = my + off_cost(C);
+  double* aU = my + g_off_U(C);
+  double* agc = my + g_off_gc(C);
+  double* aw = my + g_off_w(C);
+  double* asc = my + g_off_sc(C);
 
   for (int base = blockIdx.x * kBAThreads; base < TJ; base += gridDim.x * kBAThreads) {
     const int g = base + threadIdx.x;
@@ -192,12 +311,9 @@ ba_linearize_kernel(const double* __restrict__ intr, const double2* __restrict__
     }
     double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     double gp[3] = {0, 0, 0};
-    double W[DF3D_MAX_CAMS][6][3];
     unsigned mask = 0;
     double cost = 0.0;
     int nobs = 0;
-
-    // pass 1: per-camera blocks, V, gp, W
     for (int c = 0; c < C; ++c) {
       bool vis = false;
       double2 xy = make_double2(0.0, 0.0);
@@ -227,6 +343,190 @@ ba_linearize_kernel(const double* __restrict__ intr, const double2* __restrict__
         }
       }
 #pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double gv = warp_sum(Jc[0][i] * r[0] + Jc[1][i] * r[1]);
+        if (lane == 0) agc[c * 6 + i] += gv;
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+          const double uv = warp_sum(Jc[0][i] * Jc[0][j] + Jc[1][i] * Jc[1][j]);
+          if (lane == 0) aU[c * 36 + i * 6 + j] += uv;
+        }
+      }
+    }
+    // Jacobi scaling of the point columns: column norm, running maximum (SciPy compute_jac_scale)
+    double b[3] = {0, 0, 0}, ggp = 0.0, bVb = 0.0, dsq = 0.0, gmax = 0.0;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double cn = sqrt(V[i][i]);
+        double s = first ? (cn == 0.0 ? 1.0 : cn) : fmax(ws.sinv_p[(size_t)g * 3 + i], cn);
+        ws.sinv_p[(size_t)g * 3 + i] = s;
+        ws.gp[(size_t)g * 3 + i] = gp[i];
+        b[i] = gp[i] / (s * s);
+        ggp += (gp[i] / s) * (gp[i] / s);
+        dsq += (X[i] * s) * (X[i] * s);
+        gmax = fmax(gmax, fabs(gp[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) bVb += b[i] * (V[i][0] * b[0] + V[i][1] * b[1] + V[i][2] * b[2]);
+    }
+    // w_c = sum_obs Jc^T (Jp b): the cross term of |J_h g_h|^2
+    for (int c = 0; c < C; ++c) {
+      const bool vis = (mask >> c) & 1u;
+      if (!__any_sync(0xffffffffu, vis)) continue;
+      double wv[6] = {0, 0, 0, 0, 0, 0};
+      if (vis) {
+        const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
+        double r[2], Jc[2][6], Jp[2][3];
+        project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+        const double q0 = Jp[0][0] * b[0] + Jp[0][1] * b[1] + Jp[0][2] * b[2];
+        const double q1 = Jp[1][0] * b[0] + Jp[1][1] * b[1] + Jp[1][2] * b[2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) wv[i] = Jc[0][i] * q0 + Jc[1][i] * q1;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum(wv[i]);
+        if (lane == 0) aw[c * 6 + i] += v;
+      }
+    }
+    const double cs = warp_sum(cost), ns = warp_sum((double)nobs), bs = warp_sum(bVb), gs = warp_sum(ggp), ds = warp_sum(dsq);
+    const double gm = warp_max(gmax);
+    if (lane == 0) {
+      asc[0] += 0.5 * cs;
+      asc[1] += ns;
+      asc[2] += bs;
+      asc[3] += gs;
+      asc[4] += ds;
+      asc[5] = fmax(asc[5], gm);
+    }
+  }
+  block_partial(s_t, n_sum, n, ws.partials + (size_t)blockIdx.x * n);
+  if (!reduce_partials_last_block(ws.partials, n_sum, n, ws.red, ws.counters + 0)) return;
+  if (threadIdx.x != 0) return;
+  // ---- last block, one thread: camera scaling, gradient norms, Cauchy-step regularisation
+  const double* red = ws.red;
+  const double* U = red + g_off_U(C);
+  const double* gc = red + g_off_gc(C);
+  const double* w = red + g_off_w(C);
+  const double* sc = red + g_off_sc(C);
+  const int n6 = 6 * C;
+  double gg = sc[3], gmax = sc[5], dsq = sc[4];
+  double aUa = 0.0, aw2 = 0.0;
+  for (int i = 0; i < n6; ++i) {
+    const int c = i / 6, k = i % 6;
+    const double cn = sqrt(U[c * 36 + k * 6 + k]);
+    const double s = first ? (cn == 0.0 ? 1.0 : cn) : fmax(ws.sinv_c[i], cn);
+    ws.sinv_c[i] = s;
+    ws.gc[i] = gc[i];
+    ws.ac[i] = gc[i] / (s * s);
+    ws.ghc[i] = gc[i] / s;
+    gg += ws.ghc[i] * ws.ghc[i];
+    gmax = fmax(gmax, fabs(gc[i]));
+    dsq += (ws.cam[i] * s) * (ws.cam[i] * s);
+  }
+  for (int c = 0; c < C; ++c)
+    for (int i = 0; i < 6; ++i) {
+      double row = 0.0;
+      for (int j = 0; j < 6; ++j) {
+        const double u = i <= j ? U[c * 36 + i * 6 + j] : U[c * 36 + j * 6 + i];
+        row += u * ws.ac[c * 6 + j];
+      }
+      aUa += ws.ac[c * 6 + i] * row;
+      aw2 += ws.ac[c * 6 + i] * w[c * 6 + i];
+    }
+  const double JgJg = aUa + 2.0 * aw2 + sc[2];
+  if (first) {
+    st->F = st->F0 = sc[0];
+    st->n_obs = (int)(sc[1] + 0.5);
+    st->Delta = sqrt(dsq);
+    if (st->Delta == 0.0) st->Delta = 1.0;
+    st->first = 0;
+  }
+  st->gg = gg;
+  st->JgJg = JgJg;
+  if (st->n_obs == 0 || gmax < st->gtol) {  // trf: g_norm < gtol
+    st->done = 1;
+    st->status = 1;
+    return;
+  }
+  // reg_term = -min_{0 <= t <= Delta / |g_h|} (a t^2 + b t) / Delta^2,  a = |J_h g_h|^2 / 2, b = -|g_h|^2
+  const double a = 0.5 * JgJg, bq = -gg;
+  const double to_tr = st->Delta / sqrt(gg);
+  double best = fmin(0.0, to_tr * (a * to_tr + bq));
+  if (a != 0.0) {
+    const double ext = -0.5 * bq / a;
+    if (ext > 0.0 && ext < to_tr) best = fmin(best, ext * (a * ext + bq));
+  }
+  st->reg = -best / (st->Delta * st->Delta);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dynamic shared memory: cams [C*kCamStride] | per-warp system tiles [kBAWarps * sys_doubles(C)]
+__global__ void __launch_bounds__(kBAThreads)
+ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
+                const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws) {
+  extern __shared__ double smem[];
+  if (ws.state->done || !ws.state->need_lin) return;
+  const double reg = ws.state->reg;
+  const int nsys = sys_doubles(C);
+  const int n6 = 6 * C;
+  double* s_cam = smem;
+  double* s_sys = smem + C * kCamStride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* my = s_sys + warp * nsys;  // this warp's accumulator tile
+
+  if (threadIdx.x < C) stage_camera(ws.cam + threadIdx.x * 6, intr + threadIdx.x * 4, s_cam + threadIdx.x * kCamStride);
+  for (int e = threadIdx.x; e < kBAWarps * nsys; e += kBAThreads) s_sys[e] = 0.0;
+  __syncthreads();
+
+  double* aU = my + off_U(C);
+  double* agc = my + off_gc(C);
+  double* aS = my + off_S(C);
+  double* ab = my + off_b(C);
+
+  for (int base = blockIdx.x * kBAThreads; base < TJ; base += gridDim.x * kBAThreads) {
+    const int g = base + threadIdx.x;
+    const bool valid = g < TJ;
+    double X[3] = {0.0, 0.0, 0.0};
+    if (valid) {
+      X[0] = pts3d[(size_t)g * 3 + 0];
+      X[1] = pts3d[(size_t)g * 3 + 1];
+      X[2] = pts3d[(size_t)g * 3 + 2];
+    }
+    double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double gp[3] = {0, 0, 0};
+    double W[DF3D_MAX_CAMS][6][3];
+    unsigned mask = 0;
+
+    // pass 1: per-camera blocks, V, gp, W
+    for (int c = 0; c < C; ++c) {
+      bool vis = false;
+      double2 xy = make_double2(0.0, 0.0);
+      if (valid) {
+        xy = __ldg(pts_xy + (size_t)c * TJ + g);
+        vis = (xy.x != 0.0) && (xy.y != 0.0);
+      }
+      if (!__any_sync(0xffffffffu, vis)) continue;
+      double r[2] = {0, 0}, Jc[2][6], Jp[2][3];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Jc[a][i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Jp[a][i] = 0.0;
+      }
+      if (vis) {
+        project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+        mask |= 1u << c;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          gp[i] += Jp[0][i] * r[0] + Jp[1][i] * r[1];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) V[i][j] += Jp[0][i] * Jp[0][j] + Jp[1][i] * Jp[1][j];
+        }
+      }
+#pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) W[c][i][j] = Jc[0][i] * Jp[0][j] + Jc[1][i] * Jp[1][j];
@@ -243,28 +543,22 @@ ba_linearize_kernel(const double* __restrict__ intr, const double2* __restrict__
       }
     }
 
-    // point scaling (running max of column norms, SciPy compute_jac_scale) and M = D (DVD + lam I)^-1 D
+    // M = D (D V D + reg I)^-1 D with the point scaling fixed by ba_gradient
     double Mm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    if (valid) {
+    if (valid && mask) {
       double d[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double s = fmax(ws.sinv_p[(size_t)g * 3 + i], sqrt(V[i][i]));
-        ws.sinv_p[(size_t)g * 3 + i] = s;
-        d[i] = (s == 0.0) ? 1.0 : 1.0 / s;
-      }
-      if (mask) {
-        double Vh[3][3], Vi[3][3];
+      for (int i = 0; i < 3; ++i) d[i] = 1.0 / ws.sinv_p[(size_t)g * 3 + i];
+      double Vh[3][3], Vi[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? reg : 0.0);
+      if (inv3_spd(Vh, Vi)) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? lambda : 0.0);
-        if (inv3_sym(Vh, Vi)) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Mm[i][j] = d[i] * Vi[i][j] * d[j];
-        }
+          for (int j = 0; j < 3; ++j) Mm[i][j] = d[i] * Vi[i][j] * d[j];
       }
     }
 
@@ -296,50 +590,31 @@ ba_linearize_kernel(const double* __restrict__ intr, const double2* __restrict__
           }
       }
     }
-    const double cs = warp_sum(cost);
-    const double ns = warp_sum((double)nobs);
-    if (lane == 0) {
-      acost[0] += 0.5 * cs;
-      acost[1] += ns;
-    }
   }
-  __syncthreads();
-  // block partial = fixed-order sum of the warp tiles
-  double* part = ws.partials + (size_t)blockIdx.x * nsys;
-  for (int e = threadIdx.x; e < nsys; e += kBAThreads) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < kBAWarps; ++w) acc += s_sys[w * nsys + e];
-    part[e] = acc;
-  }
-  reduce_partials_last_block(ws.partials, nsys, sys_out, ws.counters + 0);
+  block_partial(s_sys, nsys, nsys, ws.partials + (size_t)blockIdx.x * nsys);
+  reduce_partials_last_block(ws.partials, nsys, nsys, ws.red, ws.counters + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA.  Builds and solves the scaled reduced camera system.
+// One CTA.  Builds and solves the scaled reduced camera system for the camera part of gn_h.
 constexpr int kSolveThreads = 256;
-constexpr int kMaxN = 6 * DF3D_MAX_CAMS;
 
-__global__ void __launch_bounds__(kSolveThreads)
-ba_solve_kernel(int C, BAWorkspace ws, const double* __restrict__ sys) {
-  __shared__ double A[kMaxN][kMaxN + 1];
-  __shared__ double rhs[kMaxN];
+__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(int C, BAWorkspace ws) {
+  __shared__ double A[kMaxN][kMaxN + 1];   // Cholesky factor (lower) after the factorisation
+  __shared__ double A0[kMaxN][kMaxN + 1];  // the matrix itself, for the refinement step
+  __shared__ double rhs[kMaxN], sol[kMaxN], res[kMaxN];
   __shared__ double dsc[kMaxN];
   BAState* st = ws.state;
-  if (st->done) return;
+  if (st->done || !st->need_lin) return;
   const int n = 6 * C;
-  const double lambda = st->lambda;
+  const double reg = st->reg;
+  const double* sys = ws.red;
   const double* U = sys + off_U(C);
   const double* gc = sys + off_gc(C);
   const double* S = sys + off_S(C);
   const double* bt = sys + off_b(C);
 
-  if (threadIdx.x < n) {
-    const int c = threadIdx.x / 6, i = threadIdx.x % 6;
-    double s = fmax(ws.sinv_c[threadIdx.x], sqrt(U[c * 36 + i * 6 + i]));
-    ws.sinv_c[threadIdx.x] = s;
-    dsc[threadIdx.x] = (s == 0.0) ? 1.0 : 1.0 / s;
-  }
+  if (threadIdx.x < n) dsc[threadIdx.x] = 1.0 / ws.sinv_c[threadIdx.x];
   __syncthreads();
   for (int e = threadIdx.x; e < n * n; e += kSolveThreads) {
     const int row = e / n, col = e % n;
@@ -350,10 +625,11 @@ ba_solve_kernel(int C, BAWorkspace ws, const double* __restrict__ sys) {
       v += U[c * 36 + (lo % 6) * 6 + (hi % 6)];
     }
     v *= dsc[row] * dsc[col];
-    if (row == col) v += lambda;
+    if (row == col) v += reg;
     A[row][col] = v;
+    A0[row][col] = v;
   }
-  if (threadIdx.x < n) rhs[threadIdx.x] = dsc[threadIdx.x] * (-gc[threadIdx.x] + bt[threadIdx.x]);
+  if (threadIdx.x < n) rhs[threadIdx.x] = dsc[threadIdx.x] * (gc[threadIdx.x] - bt[threadIdx.x]);
   __syncthreads();
 
   // in-place Cholesky A = L L^T (lower), right-looking, one column per step
@@ -370,156 +646,281 @@ ba_solve_kernel(int C, BAWorkspace ws, const double* __restrict__ sys) {
     }
     __syncthreads();
   }
-  // forward / backward substitution by one thread (n <= 48)
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < n; ++i) {
-      double acc = rhs[i];
-      for (int j = 0; j < i; ++j) acc -= A[i][j] * rhs[j];
-      rhs[i] = acc / A[i][i];
+  // solve, then one step of iterative refinement (the system carries eigenvalues down to `reg`: the gauge
+  // directions and cameras without observations)
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      if (threadIdx.x < n) {
+        double acc = rhs[threadIdx.x];
+        for (int j = 0; j < n; ++j) acc -= A0[threadIdx.x][j] * sol[j];
+        res[threadIdx.x] = acc;
+      }
+    } else if (threadIdx.x < n) {
+      res[threadIdx.x] = rhs[threadIdx.x];
     }
-    for (int i = n - 1; i >= 0; --i) {
-      double acc = rhs[i];
-      for (int j = i + 1; j < n; ++j) acc -= A[j][i] * rhs[j];
-      rhs[i] = acc / A[i][i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < n; ++i) {
+        double acc = res[i];
+        for (int j = 0; j < i; ++j) acc -= A[i][j] * res[j];
+        res[i] = acc / A[i][i];
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        double acc = res[i];
+        for (int j = i + 1; j < n; ++j) acc -= A[j][i] * res[j];
+        res[i] = acc / A[i][i];
+      }
     }
-    if (st->iter == 0 && st->F < 0.0) {
-      st->F = st->F0 = sys[off_cost(C)];
-      st->n_obs = (int)(sys[off_cost(C) + 1] + 0.5);
-    }
+    __syncthreads();
+    if (threadIdx.x < n) sol[threadIdx.x] = pass == 0 ? res[threadIdx.x] : sol[threadIdx.x] + res[threadIdx.x];
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x < n) {
-    const double d = dsc[threadIdx.x] * rhs[threadIdx.x];
-    ws.dcam[threadIdx.x] = d;
-    ws.cam_new[threadIdx.x] = ws.cam[threadIdx.x] + d;
+    ws.gnc[threadIdx.x] = sol[threadIdx.x];
+    ws.dcn[threadIdx.x] = dsc[threadIdx.x] * sol[threadIdx.x];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Back-substitution + candidate cost.  dynamic smem: cams (old) | cams (new) | dcam
+// Point part of gn_h + Gram quantities.  dynamic smem: cams | ac [6C] | dcn [6C] | tiles [kBAWarps * 4]
 __global__ void __launch_bounds__(kBAThreads)
-ba_evaluate_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
-                   const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws, double* __restrict__ cost_out) {
+ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
+                  const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws) {
   extern __shared__ double smem[];
-  if (ws.state->done) return;
-  const double lambda = ws.state->lambda;
-  double* s_old = smem;
-  double* s_new = smem + C * kCamStride;
-  double* s_dc = s_new + C * kCamStride;
-  __shared__ double s_part[kBAWarps];
-  if (threadIdx.x < C) {
-    stage_camera(ws.cam + threadIdx.x * 6, intr + threadIdx.x * 4, s_old + threadIdx.x * kCamStride);
-    stage_camera(ws.cam_new + threadIdx.x * 6, intr + threadIdx.x * 4, s_new + threadIdx.x * kCamStride);
+  BAState* st = ws.state;
+  if (st->done || !st->need_lin) return;
+  const double reg = st->reg;
+  double* s_cam = smem;
+  double* s_ac = smem + C * kCamStride;
+  double* s_dc = s_ac + 6 * C;
+  double* s_t = s_dc + 6 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < C) stage_camera(ws.cam + threadIdx.x * 6, intr + threadIdx.x * 4, s_cam + threadIdx.x * kCamStride);
+  if (threadIdx.x < 6 * C) {
+    s_ac[threadIdx.x] = ws.ac[threadIdx.x];
+    s_dc[threadIdx.x] = ws.dcn[threadIdx.x];
   }
-  if (threadIdx.x < 6 * C) s_dc[threadIdx.x] = ws.dcam[threadIdx.x];
+  if (threadIdx.x < kBAWarps * 4) s_t[threadIdx.x] = 0.0;
   __syncthreads();
 
-  double cost = 0.0;
+  double a_ggn = 0.0, a_gngn = 0.0, a_JgJgn = 0.0, a_JgnJgn = 0.0;
   for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += gridDim.x * kBAThreads) {
-    double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
+    const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
     double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    double rhs[3] = {0, 0, 0};  // -(g_p + sum_c W_c^T dc)
+    double rp[3] = {0, 0, 0};  // sum Jp^T (r - Jc dcn)
     unsigned mask = 0;
     for (int c = 0; c < C; ++c) {
       const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
       if (xy.x == 0.0 || xy.y == 0.0) continue;
       mask |= 1u << c;
       double r[2], Jc[2][6], Jp[2][3];
-      project_jacobian(s_old + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
-      // r + Jc dc  (first-order residual after the camera step)
+      project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
       double q[2];
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         double acc = r[a];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) acc += Jc[a][i] * s_dc[c * 6 + i];
+        for (int i = 0; i < 6; ++i) acc -= Jc[a][i] * s_dc[c * 6 + i];
         q[a] = acc;
       }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        rhs[i] -= Jp[0][i] * q[0] + Jp[1][i] * q[1];
+        rp[i] += Jp[0][i] * q[0] + Jp[1][i] * q[1];
 #pragma unroll
         for (int j = 0; j < 3; ++j) V[i][j] += Jp[0][i] * Jp[0][j] + Jp[1][i] * Jp[1][j];
       }
     }
-    double Xn[3] = {X[0], X[1], X[2]};
-    if (mask) {
-      double d[3];
+    double pp[3] = {0, 0, 0};  // scaled point part of gn_h
+    double d[3], gh[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double s = ws.sinv_p[(size_t)g * 3 + i];  // already updated by ba_linearize
-        d[i] = (s == 0.0) ? 1.0 : 1.0 / s;
-      }
+    for (int i = 0; i < 3; ++i) {
+      d[i] = 1.0 / ws.sinv_p[(size_t)g * 3 + i];
+      gh[i] = ws.gp[(size_t)g * 3 + i] * d[i];
+    }
+    if (mask) {
       double Vh[3][3], Vi[3][3];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? lambda : 0.0);
-      if (inv3_sym(Vh, Vi)) {
+        for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? reg : 0.0);
+      if (inv3_spd(Vh, Vi)) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) acc += d[i] * Vi[i][j] * d[j] * rhs[j];
-          Xn[i] += acc;
-        }
+        for (int i = 0; i < 3; ++i) pp[i] = Vi[i][0] * d[0] * rp[0] + Vi[i][1] * d[1] * rp[1] + Vi[i][2] * d[2] * rp[2];
       }
     }
-    ws.X_new[(size_t)g * 3 + 0] = Xn[0];
-    ws.X_new[(size_t)g * 3 + 1] = Xn[1];
-    ws.X_new[(size_t)g * 3 + 2] = Xn[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      ws.gnp[(size_t)g * 3 + i] = pp[i];
+      a_ggn += gh[i] * pp[i];
+      a_gngn += pp[i] * pp[i];
+    }
+    // J_h g_h and J_h gn_h of this point's observations
+    const double bp[3] = {gh[0] * d[0], gh[1] * d[1], gh[2] * d[2]};
+    const double dp[3] = {pp[0] * d[0], pp[1] * d[1], pp[2] * d[2]};
     for (int c = 0; c < C; ++c) {
       if (!((mask >> c) & 1u)) continue;
       const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
+      double r[2], Jc[2][6], Jp[2][3];
+      project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        double jg = Jp[a][0] * bp[0] + Jp[a][1] * bp[1] + Jp[a][2] * bp[2];
+        double jn = Jp[a][0] * dp[0] + Jp[a][1] * dp[1] + Jp[a][2] * dp[2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          jg += Jc[a][i] * s_ac[c * 6 + i];
+          jn += Jc[a][i] * s_dc[c * 6 + i];
+        }
+        a_JgJgn += jg * jn;
+        a_JgnJgn += jn * jn;
+      }
+    }
+  }
+  a_ggn = warp_sum(a_ggn);
+  a_gngn = warp_sum(a_gngn);
+  a_JgJgn = warp_sum(a_JgJgn);
+  a_JgnJgn = warp_sum(a_JgnJgn);
+  if (lane == 0) {
+    s_t[warp * 4 + 0] = a_ggn;
+    s_t[warp * 4 + 1] = a_gngn;
+    s_t[warp * 4 + 2] = a_JgJgn;
+    s_t[warp * 4 + 3] = a_JgnJgn;
+  }
+  block_partial(s_t, 4, 4, ws.partials + (size_t)blockIdx.x * 4);
+  if (!reduce_partials_last_block(ws.partials, 4, 4, ws.red, ws.counters + 2)) return;
+  if (threadIdx.x != 0) return;
+  // ---- last block, one thread: the 2-D sub-problem in an orthonormal basis of span{g_h, gn_h}
+  double g_gn = ws.red[0], gn_gn = ws.red[1];
+  const double Jg_Jgn = ws.red[2], Jgn_Jgn = ws.red[3];
+  for (int i = 0; i < 6 * C; ++i) {
+    g_gn += ws.ghc[i] * ws.gnc[i];
+    gn_gn += ws.gnc[i] * ws.gnc[i];
+  }
+  const double gg = st->gg, JgJg = st->JgJg;
+  const double n1 = sqrt(gg);
+  const double c12 = g_gn / n1;
+  const double n2sq = gn_gn - c12 * c12;
+  const double n2 = n2sq > 0.0 ? sqrt(n2sq) : 0.0;
+  st->T00 = 1.0 / n1;
+  if (n2 > 1e-14 * sqrt(gn_gn)) {
+    st->T10 = -c12 / (n1 * n2);
+    st->T11 = 1.0 / n2;
+  } else {
+    st->T10 = st->T11 = 0.0;
+  }
+  // B_S = T Bg T^T with Bg = [[JgJg, Jg_Jgn], [Jg_Jgn, Jgn_Jgn]];  g_S = T [gg, g_gn]
+  const double t00 = st->T00, t10 = st->T10, t11 = st->T11;
+  st->B00 = t00 * t00 * JgJg;
+  st->B01 = t00 * (t10 * JgJg + t11 * Jg_Jgn);
+  st->B11 = t10 * t10 * JgJg + 2.0 * t10 * t11 * Jg_Jgn + t11 * t11 * Jgn_Jgn;
+  st->gS0 = t00 * gg;
+  st->gS1 = t10 * gg + t11 * g_gn;
+  solve_subproblem(st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate x + D step_h and its cost; the last block decides.  dynamic smem: cams (new) | cam_new [6C]
+__global__ void __launch_bounds__(kBAThreads)
+ba_step_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
+               const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws) {
+  extern __shared__ double smem[];
+  BAState* st = ws.state;
+  if (st->done) return;
+  double* s_new = smem;
+  double* s_cn = smem + C * kCamStride;
+  double* s_t = s_cn + 6 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double cg = st->coef_g, cn = st->coef_gn;
+  if (threadIdx.x < 6 * C)
+    s_cn[threadIdx.x] = ws.cam[threadIdx.x] + (cg * ws.ghc[threadIdx.x] + cn * ws.gnc[threadIdx.x]) / ws.sinv_c[threadIdx.x];
+  if (threadIdx.x < kBAWarps * 3) s_t[threadIdx.x] = 0.0;
+  __syncthreads();
+  if (threadIdx.x < C) stage_camera(s_cn + threadIdx.x * 6, intr + threadIdx.x * 4, s_new + threadIdx.x * kCamStride);
+  __syncthreads();
+
+  double cost = 0.0, stepsq = 0.0, xsq = 0.0;
+  for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += gridDim.x * kBAThreads) {
+    double Xn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double x = pts3d[(size_t)g * 3 + i];
+      const double s = ws.sinv_p[(size_t)g * 3 + i];
+      const double step = (cg * (ws.gp[(size_t)g * 3 + i] / s) + cn * ws.gnp[(size_t)g * 3 + i]) / s;
+      Xn[i] = x + step;
+      stepsq += step * step;
+      xsq += x * x;
+      ws.X_new[(size_t)g * 3 + i] = Xn[i];
+    }
+    for (int c = 0; c < C; ++c) {
+      const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
+      if (xy.x == 0.0 || xy.y == 0.0) continue;
       double r[2];
       project_residual(s_new + c * kCamStride, Xn, xy.x, xy.y, r);
       cost += r[0] * r[0] + r[1] * r[1];
     }
   }
   cost = warp_sum(cost);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = cost;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < kBAWarps; ++w) acc += s_part[w];
-    ws.cost_partials[blockIdx.x * 2 + 0] = 0.5 * acc;
-    ws.cost_partials[blockIdx.x * 2 + 1] = 0.0;
+  stepsq = warp_sum(stepsq);
+  xsq = warp_sum(xsq);
+  if (lane == 0) {
+    s_t[warp * 3 + 0] = 0.5 * cost;
+    s_t[warp * 3 + 1] = stepsq;
+    s_t[warp * 3 + 2] = xsq;
   }
-  reduce_partials_last_block(ws.cost_partials, 2, cost_out, ws.counters + 1);
-}
-
-__global__ void ba_decide_kernel(int C, BAWorkspace ws, const double* __restrict__ cost) {
-  BAState* st = ws.state;
+  block_partial(s_t, 3, 3, ws.partials + (size_t)blockIdx.x * 3);
+  if (!reduce_partials_last_block(ws.partials, 3, 3, ws.red, ws.counters + 3)) return;
   if (threadIdx.x != 0) return;
-  st->accept_flag = 0;
-  if (st->done) return;
-  const double Fn = cost[0];
-  st->iter += 1;
-  if (st->n_obs == 0) {
-    st->done = 1;
-    st->status = 1;
-    return;
+  // ---- last block, one thread: trf_no_bounds' inner loop body after f_new = fun(x_new)
+  const double Fn = ws.red[0];
+  double stepsq_t = ws.red[1], xsq_t = ws.red[2];
+  for (int i = 0; i < 6 * C; ++i) {
+    const double d = s_cn[i] - ws.cam[i];
+    stepsq_t += d * d;
+    xsq_t += ws.cam[i] * ws.cam[i];
   }
-  if (Fn < st->F) {
-    const double dF = st->F - Fn;
-    const double Fold = st->F;
-    st->F = Fn;
-    st->accepted += 1;
-    st->accept_flag = 1;
-    for (int i = 0; i < 6 * C; ++i) ws.cam[i] = ws.cam_new[i];
-    if (dF < st->ftol * Fold) {
-      st->done = 1;
-      st->status = 1;
-    }
+  st->iter += 1;
+  st->accept_flag = 0;
+  st->need_lin = 0;
+  if (!isfinite(Fn)) {
+    st->Delta = 0.25 * st->sh_norm;
   } else {
-    st->lambda = fmin(st->lambda * 10.0, 1e8);
+    const double actual = st->F - Fn, pred = st->pred;
+    double ratio;
+    if (pred > 0.0)
+      ratio = actual / pred;
+    else if (pred == 0.0 && actual == 0.0)
+      ratio = 1.0;
+    else
+      ratio = 0.0;
+    double Delta_new = st->Delta;
+    if (ratio < 0.25)
+      Delta_new = 0.25 * st->sh_norm;
+    else if (ratio > 0.75 && st->sh_norm > 0.95 * st->Delta)
+      Delta_new = 2.0 * st->Delta;
+    const bool f_ok = actual < st->ftol * st->F && ratio > 0.25;
+    const bool x_ok = sqrt(stepsq_t) < st->xtol * (st->xtol + sqrt(xsq_t));
+    const int term = (f_ok && x_ok) ? 4 : f_ok ? 2 : x_ok ? 3 : 0;
+    if (term) {
+      st->done = 1;
+      st->status = term;
+    } else {
+      st->Delta = Delta_new;
+    }
+    if (actual > 0.0) {
+      st->F = Fn;
+      st->accepted += 1;
+      st->accept_flag = st->iter;
+      st->need_lin = 1;
+      for (int i = 0; i < 6 * C; ++i) ws.cam[i] = s_cn[i];
+    }
   }
   if (st->iter >= st->max_iters) st->done = 1;
+  if (!st->done && !st->need_lin) solve_subproblem(st);  // rejected: same model, smaller region
 }
 
-__global__ void ba_apply_points_kernel(int n, BAWorkspace ws, double* __restrict__ pts3d) {
-  if (!ws.state->accept_flag) return;
+// accept_flag holds the number of the iteration whose candidate was accepted (0: none)
+__global__ void ba_apply_points_kernel(int n, int iter, BAWorkspace ws, double* __restrict__ pts3d) {
+  if (ws.state->accept_flag != iter) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pts3d[i] = ws.X_new[i];
 }
 
@@ -529,7 +930,7 @@ __global__ void ba_end_kernel(double* __restrict__ cam_rt, int C, BAWorkspace ws
     const BAState s = *ws.state;
     report->cost0 = s.F0;
     report->cost = s.F;
-    report->lambda = s.lambda;
+    report->reg = s.reg;
     report->iters = s.iter;
     report->accepted = s.accepted;
     report->n_obs = s.n_obs;
@@ -580,94 +981,9 @@ extern "C" size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J) {
   return ba_workspace_layout(C, T, J, nullptr, nullptr) + 256;
 }
 
-extern "C" size_t df3d_ba_system_doubles(int C) { return (C < 1 || C > DF3D_MAX_CAMS) ? 0 : (size_t)sys_doubles(C); }
-
-static int get_ws(const char* fn, int C, int T, int J, void* workspace_dev, size_t workspace_bytes, BAWorkspace* ws) {
-  DF3D_REQUIRE(workspace_dev, DF3D_EINVAL, "%s: null workspace", fn);
-  DF3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, DF3D_EINVAL, "%s: workspace must be 256-byte aligned", fn);
-  const size_t need = ba_workspace_layout(C, T, J, static_cast<char*>(workspace_dev), ws);
-  if (workspace_bytes != (size_t)-1)
-    DF3D_REQUIRE(workspace_bytes >= need, DF3D_ENOMEM, "%s: workspace too small (%zu < %zu bytes)", fn, workspace_bytes, need);
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_begin(const double* cam_rt_dev, const df3d_ba_opts* opts, int C, int T, int J,
-                             void* workspace_dev, size_t workspace_bytes, void* stream) {
-  if (int e = check_common("df3d_ba_begin", C, T, J)) return e;
-  DF3D_REQUIRE(cam_rt_dev, DF3D_EINVAL, "df3d_ba_begin: null pointer");
-  df3d_ba_opts o{20, 1e-4, 1e-6};
-  if (opts) o = *opts;
-  DF3D_REQUIRE(o.max_iters >= 1 && o.max_iters <= 1000 && o.ftol >= 0.0 && o.lambda0 > 0.0, DF3D_EINVAL,
-               "df3d_ba_begin: bad options (max_iters in [1,1000], ftol >= 0, lambda0 > 0)");
-  BAWorkspace ws;
-  if (int e = get_ws("df3d_ba_begin", C, T, J, workspace_dev, workspace_bytes, &ws)) return e;
-  ba_begin_kernel<<<ba_grid(T * J), kBAThreads, 0, static_cast<cudaStream_t>(stream)>>>(cam_rt_dev, C, T * J, o, ws);
-  DF3D_LAUNCH_CHECK("ba_begin_kernel");
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_linearize(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
-                                 int C, int T, int J, void* workspace_dev, double* sys_dev, void* stream) {
-  if (int e = check_common("df3d_ba_linearize", C, T, J)) return e;
-  DF3D_REQUIRE(intr_dev && pts_xy_dev && pts3d_dev && sys_dev, DF3D_EINVAL, "df3d_ba_linearize: null pointer");
-  BAWorkspace ws;
-  if (int e = get_ws("df3d_ba_linearize", C, T, J, workspace_dev, (size_t)-1, &ws)) return e;
-  const size_t smem = ((size_t)C * kCamStride + (size_t)kBAWarps * sys_doubles(C)) * sizeof(double);
-  DF3D_CUDA(cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ba_linearize_kernel<<<ba_grid(T * J), kBAThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      intr_dev, reinterpret_cast<const double2*>(pts_xy_dev), pts3d_dev, C, T * J, ws, sys_dev);
-  DF3D_LAUNCH_CHECK("ba_linearize_kernel");
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_solve(int C, void* workspace_dev, const double* sys_dev, void* stream) {
-  DF3D_REQUIRE(C >= 1 && C <= DF3D_MAX_CAMS, DF3D_EINVAL, "df3d_ba_solve: C must be in [1,%d]", DF3D_MAX_CAMS);
-  DF3D_REQUIRE(workspace_dev && sys_dev, DF3D_EINVAL, "df3d_ba_solve: null pointer");
-  BAWorkspace ws;
-  ba_workspace_layout(C, 1, 1, static_cast<char*>(workspace_dev), &ws);  // camera-side fields do not depend on T,J
-  ba_solve_kernel<<<1, kSolveThreads, 0, static_cast<cudaStream_t>(stream)>>>(C, ws, sys_dev);
-  DF3D_LAUNCH_CHECK("ba_solve_kernel");
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_evaluate(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
-                                int C, int T, int J, void* workspace_dev, double* cost_dev, void* stream) {
-  if (int e = check_common("df3d_ba_evaluate", C, T, J)) return e;
-  DF3D_REQUIRE(intr_dev && pts_xy_dev && pts3d_dev && cost_dev, DF3D_EINVAL, "df3d_ba_evaluate: null pointer");
-  BAWorkspace ws;
-  if (int e = get_ws("df3d_ba_evaluate", C, T, J, workspace_dev, (size_t)-1, &ws)) return e;
-  const size_t smem = ((size_t)2 * C * kCamStride + 6 * C) * sizeof(double);
-  ba_evaluate_kernel<<<ba_grid(T * J), kBAThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      intr_dev, reinterpret_cast<const double2*>(pts_xy_dev), pts3d_dev, C, T * J, ws, cost_dev);
-  DF3D_LAUNCH_CHECK("ba_evaluate_kernel");
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_decide(int C, int T, int J, void* workspace_dev, const double* cost_dev,
-                              double* pts3d_dev, void* stream) {
-  if (int e = check_common("df3d_ba_decide", C, T, J)) return e;
-  DF3D_REQUIRE(cost_dev && pts3d_dev, DF3D_EINVAL, "df3d_ba_decide: null pointer");
-  BAWorkspace ws;
-  if (int e = get_ws("df3d_ba_decide", C, T, J, workspace_dev, (size_t)-1, &ws)) return e;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ba_decide_kernel<<<1, 32, 0, s>>>(C, ws, cost_dev);
-  DF3D_LAUNCH_CHECK("ba_decide_kernel");
-  const int n = T * J * 3;
-  int grid = ceil_div(n, 256);
-  if (grid > 4 * kBAMaxBlocks) grid = 4 * kBAMaxBlocks;
-  ba_apply_points_kernel<<<grid, 256, 0, s>>>(n, ws, pts3d_dev);
-  DF3D_LAUNCH_CHECK("ba_apply_points_kernel");
-  return DF3D_OK;
-}
-
-extern "C" int df3d_ba_end(double* cam_rt_dev, int C, void* workspace_dev, df3d_ba_report* report_dev, void* stream) {
-  DF3D_REQUIRE(C >= 1 && C <= DF3D_MAX_CAMS, DF3D_EINVAL, "df3d_ba_end: C must be in [1,%d]", DF3D_MAX_CAMS);
-  DF3D_REQUIRE(cam_rt_dev && workspace_dev, DF3D_EINVAL, "df3d_ba_end: null pointer");
-  BAWorkspace ws;
-  ba_workspace_layout(C, 1, 1, static_cast<char*>(workspace_dev), &ws);
-  ba_end_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(cam_rt_dev, C, ws, report_dev);
-  DF3D_LAUNCH_CHECK("ba_end_kernel");
-  return DF3D_OK;
+extern "C" int df3d_bundle_adjust_launches(const df3d_ba_opts* opts) {
+  const int iters = opts ? opts->max_iters : 20;
+  return 2 + 6 * iters;
 }
 
 extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double* pts_xy_dev,
@@ -677,19 +993,42 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
   if (int e = check_common("df3d_bundle_adjust", C, T, J)) return e;
   DF3D_REQUIRE(cam_rt_dev && intr_dev && pts_xy_dev && pts3d_dev, DF3D_EINVAL, "df3d_bundle_adjust: null pointer");
   DF3D_REQUIRE((reinterpret_cast<uintptr_t>(pts_xy_dev) & 15) == 0, DF3D_EINVAL, "df3d_bundle_adjust: pts_xy must be 16-byte aligned");
+  DF3D_REQUIRE(workspace_dev, DF3D_EINVAL, "df3d_bundle_adjust: null workspace");
+  DF3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, DF3D_EINVAL, "df3d_bundle_adjust: workspace must be 256-byte aligned");
   BAWorkspace ws;
-  if (int e = get_ws("df3d_bundle_adjust", C, T, J, workspace_dev, workspace_bytes, &ws)) return e;
-  df3d_ba_opts o{20, 1e-4, 1e-6};
+  const size_t need = ba_workspace_layout(C, T, J, static_cast<char*>(workspace_dev), &ws);
+  DF3D_REQUIRE(workspace_bytes >= need, DF3D_ENOMEM, "df3d_bundle_adjust: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  df3d_ba_opts o{20, 1e-4, 1e-8, 1e-8};
   if (opts) o = *opts;
-  if (int e = df3d_ba_begin(cam_rt_dev, &o, C, T, J, workspace_dev, workspace_bytes, stream)) return e;
+  DF3D_REQUIRE(o.max_iters >= 1 && o.max_iters <= 1000 && o.ftol >= 0.0 && o.xtol >= 0.0 && o.gtol >= 0.0, DF3D_EINVAL,
+               "df3d_bundle_adjust: bad options (max_iters in [1,1000], tolerances >= 0)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int TJ = T * J;
+  const int grid = ba_grid(TJ);
+  const size_t smem_g = ((size_t)C * kCamStride + (size_t)kBAWarps * g_doubles(C)) * sizeof(double);
+  const size_t smem_s = ((size_t)C * kCamStride + (size_t)kBAWarps * sys_doubles(C)) * sizeof(double);
+  const size_t smem_b = ((size_t)C * kCamStride + 12 * C + kBAWarps * 4) * sizeof(double);
+  const size_t smem_e = ((size_t)C * kCamStride + 6 * C + kBAWarps * 3) * sizeof(double);
+  DF3D_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+  const double2* xy = reinterpret_cast<const double2*>(pts_xy_dev);
+  ba_begin_kernel<<<1, 64, 0, s>>>(cam_rt_dev, C, o, ws);
+  DF3D_LAUNCH_CHECK("ba_begin_kernel");
+  const int n3 = TJ * 3;
+  int agrid = ceil_div(n3, 256);
+  if (agrid > 4 * kBAMaxBlocks) agrid = 4 * kBAMaxBlocks;
   // fixed launch sequence; kernels become no-ops once the device-side state says `done`
   for (int it = 0; it < o.max_iters; ++it) {
-    if (int e = df3d_ba_linearize(intr_dev, pts_xy_dev, pts3d_dev, C, T, J, workspace_dev, ws.sys_local, stream)) return e;
-    if (int e = df3d_ba_solve(C, workspace_dev, ws.sys_local, stream)) return e;
-    if (int e = df3d_ba_evaluate(intr_dev, pts_xy_dev, pts3d_dev, C, T, J, workspace_dev, ws.cost_local, stream)) return e;
-    if (int e = df3d_ba_decide(C, T, J, workspace_dev, ws.cost_local, pts3d_dev, stream)) return e;
+    ba_gradient_kernel<<<grid, kBAThreads, smem_g, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_schur_kernel<<<grid, kBAThreads, smem_s, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
+    ba_backsub_kernel<<<grid, kBAThreads, smem_b, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_step_kernel<<<grid, kBAThreads, smem_e, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, it + 1, ws, pts3d_dev);
+    DF3D_LAUNCH_CHECK("bundle adjustment iteration");
   }
-  return df3d_ba_end(cam_rt_dev, C, workspace_dev, report_dev, stream);
+  ba_end_kernel<<<1, 64, 0, s>>>(cam_rt_dev, C, ws, report_dev);
+  DF3D_LAUNCH_CHECK("ba_end_kernel");
+  return DF3D_OK;
 }
 
 extern "C" int df3d_reprojection_error(const double* cam_rt_dev, const double* intr_dev,

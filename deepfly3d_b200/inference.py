@@ -7,12 +7,17 @@
                             network frame
     conf     (7, T, 19, 1)  float32 peak value
 
-Image ingest: by default the JPEG files are decoded on the host (the
-reference's path too, bit-identical frames); `gpu_decode=True` decodes them with nvJPEG on the device (a few
-grey levels away).  The resize to the network input always runs on the device (csrc/ingest.cu, bit-identical
-to the cv2.resize(..., INTER_LINEAR) the loader used to do on the host).
+Image ingest is a bounded-memory stream, like the reference's DataLoader: the
+recording is cut into blocks of frames; a pool of host threads decodes block k+1 into pinned memory
+(``cv2.imread`` releases the GIL) while a copy stream uploads block k and the main stream resizes it to the
+network input (csrc/ingest.cu, bit-identical to ``cv2.resize(..., INTER_LINEAR)``) and runs the hourglass on it.
+Host and device memory are bounded by two blocks, whatever the length of the recording.  By default the JPEG
+files are decoded on the host (the reference's path too, bit-identical frames); ``gpu_decode=True`` decodes them
+with nvJPEG on the device (a few grey levels away).
 """
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -20,7 +25,8 @@ import torch
 from .hourglass import HourglassEngine
 from .skeleton import HEATMAP_SHAPE, NUM_CAMERAS, NUM_PREDICT
 
-_ENGINES = {}
+# images of one engine launch sequence at 256 x 256 (csrc/hourglass.cu: chunk_for); other input sizes scale by area
+_CHUNK_IMAGES_256 = 1792
 
 
 def image_name(folder, cam_id, img_id):
@@ -30,65 +36,93 @@ def image_name(folder, cam_id, img_id):
     return os.path.join(folder, f"camera_{cam_id}_img_{img_id:06d}.jpg")
 
 
-def read_images(folder, max_img_id, pin_memory=True):
-    """-> uint8 tensor (7, T, Hs, Ws): the gray frames at their native size, in pinned host memory."""
-    import cv2
-
-    T = max_img_id + 1
-    out = None
-    for c in range(NUM_CAMERAS):
-        for t in range(T):
-            path = image_name(folder, c, t)
-            img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
-            if img is None:
-                raise FileNotFoundError(f"cannot read {path}")
-            if out is None:
-                out = torch.empty((NUM_CAMERAS, T) + img.shape, dtype=torch.uint8)
-                if pin_memory and torch.cuda.is_available():
-                    out = out.pin_memory()
-                arr = out.numpy()
-            if img.shape != tuple(out.shape[2:]):
-                raise ValueError(f"{path}: image size {img.shape} differs from the first image {tuple(out.shape[2:])}")
-            arr[c, t] = img
-    return out
+def plan_blocks(T, block_frames):
+    """Frame blocks [(t0, t1), ...] covering [0, T) in order."""
+    block_frames = max(1, int(block_frames))
+    return [(t0, min(T, t0 + block_frames)) for t0 in range(0, T, block_frames)]
 
 
-_JPEG = {}
+def block_frames_for(in_h, in_w, T, batch_size=8):
+    """Frames per block: what one launch sequence of the engine takes (1 792 images at 256 x 256, scaled by the
+    input area), never less than the reference's `batch_size` images, never more than the recording."""
+    images = max(int(batch_size), (_CHUNK_IMAGES_256 * 256 * 256) // (int(in_h) * int(in_w)), NUM_CAMERAS)
+    return max(1, min(int(T), images // NUM_CAMERAS))
 
 
-def decode_images_device(folder, max_img_id, device="cuda"):
-    """-> uint8 tensor (7*T, Hs, Ws) ON THE DEVICE: the compressed files are read on the host and decoded by
-    nvJPEG (ops.JpegDecoder).  Opt-in: a few grey levels away from the host's libjpeg read."""
-    from . import ops
+class FolderReader:
+    """Threaded host-side read of ``camera_{c}_img_{t}.jpg`` frame blocks (native size, gray)."""
 
-    dec = _JPEG.get("dec")
-    if dec is None:
-        dec = _JPEG["dec"] = ops.JpegDecoder()
-    streams = []
-    for c in range(NUM_CAMERAS):
-        for t in range(max_img_id + 1):
-            path = image_name(folder, c, t)
+    def __init__(self, folder, workers=None):
+        self.folder = folder
+        self.workers = workers or min(32, os.cpu_count() or 1)
+        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="df3d-read")
+        self._shape = None
+        self._lock = threading.Lock()
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def shape(self):
+        """(H, W) of the recording's frames, from camera 0, image 0."""
+        if self._shape is None:
+            self._shape = tuple(self._decode(image_name(self.folder, 0, 0)).shape)
+        return self._shape
+
+    @staticmethod
+    def _decode(path):
+        import cv2
+
+        img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        if img is None:
+            raise FileNotFoundError(f"cannot read {path}")
+        return img
+
+    def _read_into(self, arr, c, t, slot):
+        path = image_name(self.folder, c, t)
+        img = self._decode(path)
+        if img.shape != arr.shape[2:]:
+            raise ValueError(f"{path}: image size {img.shape} differs from the first image {tuple(arr.shape[2:])}")
+        arr[c, slot] = img
+
+    def read_block_async(self, t0, t1, out):
+        """Decodes frames [t0, t1) of all cameras into out[:, :t1-t0] ((7, >=t1-t0, H, W) uint8 tensor).
+        Returns the futures; ``wait`` re-raises the first failure."""
+        arr = out.numpy()
+        return [self._pool.submit(self._read_into, arr, c, t, t - t0) for c in range(NUM_CAMERAS) for t in range(t0, t1)]
+
+    def read_bytes_async(self, t0, t1):
+        """Compressed streams of frames [t0, t1), camera-major (for the device-side decode)."""
+        def rd(c, t):
+            path = image_name(self.folder, c, t)
             if not os.path.isfile(path):
                 raise FileNotFoundError(f"cannot read {path}")
             with open(path, "rb") as f:
-                streams.append(f.read())
-    return dec.decode_gray(streams, device=device)
+                return f.read()
+        return [self._pool.submit(rd, c, t) for c in range(NUM_CAMERAS) for t in range(t0, t1)]
+
+    @staticmethod
+    def wait(futures):
+        return [f.result() for f in futures]
 
 
-def load_images(folder, max_img_id, size_hw, pin_memory=True, device="cuda", gpu_decode=False):
-    """-> uint8 tensor (7*T, H, W) gray ON THE DEVICE, resized to the network input (camera-major)."""
-    from . import ops
-
-    if gpu_decode:
-        dev = decode_images_device(folder, max_img_id, device=device)
-        Hs, Ws = dev.shape[1:]
-    else:
-        native = read_images(folder, max_img_id, pin_memory=pin_memory)
-        C, T, Hs, Ws = native.shape
-        dev = native.reshape(C * T, Hs, Ws).to(device, non_blocking=True)
-    if (Hs, Ws) != tuple(size_hw):
-        dev = ops.resize_gray_u8(dev, size_hw)
-    return dev
+def read_images(folder, max_img_id, pin_memory=True):
+    """-> uint8 tensor (7, T, Hs, Ws): the gray frames at their native size in (pinned) host memory.  Whole
+    recording at once -- small folders and tests; ``inference_folder`` streams blocks instead."""
+    T = max_img_id + 1
+    with FolderReader(folder) as rd:
+        Hs, Ws = rd.shape
+        out = torch.empty((NUM_CAMERAS, T, Hs, Ws), dtype=torch.uint8)
+        if pin_memory and torch.cuda.is_available():
+            out = out.pin_memory()
+        rd.wait(rd.read_block_async(0, T, out))
+    return out
 
 
 def random_state_dict(num_stacks=2, num_classes=NUM_PREDICT, seed=0):
@@ -128,7 +162,8 @@ def random_state_dict(num_stacks=2, num_classes=NUM_PREDICT, seed=0):
 
 
 def load_state_dict(weights=None):
-    """Checkpoint path (torch file holding a state_dict, possibly under 'state_dict') or
+    """Checkpoint path (torch file holding a state_dict, possibly under 'state_dict', keys possibly prefixed
+    with DataParallel's 'module.' -- the layout of df2d's ``sh8_deepfly.tar``, reference df3d/config.py:30-32) or
     $DF3D_B200_WEIGHTS; without either, seeded stand-in weights are used and a warning is logged."""
     path = weights or os.environ.get("DF3D_B200_WEIGHTS")
     if path:
@@ -141,42 +176,169 @@ def load_state_dict(weights=None):
     return random_state_dict()
 
 
-def get_engine(state_dict, in_h, in_w, max_batch, device="cuda"):
-    key = (id(state_dict), in_h, in_w, device)
-    eng = _ENGINES.get(key)
-    if eng is None or eng.max_batch < max_batch:
-        eng = HourglassEngine(state_dict, in_h, in_w, max_batch, device=device)
-        _ENGINES[key] = eng
-    return eng
+def load_mean(mean=None):
+    """The per-channel mean subtracted from x/255: a number, three numbers, or the path of a torch file like
+    df2d's ``mean.pth.tar`` (reference df3d/config.py:37-39: a dict with a 'mean' entry, or the bare tensor);
+    None -> $DF3D_B200_MEAN if set, else 0.5."""
+    if mean is None:
+        mean = os.environ.get("DF3D_B200_MEAN")
+        if mean is None:
+            return (0.5, 0.5, 0.5)
+    if isinstance(mean, (str, os.PathLike)):
+        if os.path.isfile(mean):
+            obj = torch.load(mean, map_location="cpu", weights_only=False)
+            if isinstance(obj, dict):
+                obj = obj["mean"]
+            mean = obj
+        else:
+            mean = float(mean)
+    m = np.asarray(mean.detach().cpu().numpy() if torch.is_tensor(mean) else mean, dtype=np.float64).reshape(-1)
+    if m.size == 1:
+        m = np.repeat(m, 3)
+    if m.size != 3:
+        raise ValueError(f"mean must have 1 or 3 entries, got {m.size}")
+    return tuple(float(v) for v in m)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine cache: ONE engine (its workspace is tens of GB), keyed on what the weights ARE, not on an object id
+_ENGINE = {"key": None, "engine": None, "ref": None}
+_ENGINE_LOCK = threading.Lock()
+
+
+def _weights_key(state_dict, weights):
+    if state_dict is not None:
+        return ("dict", id(state_dict))      # the cache entry keeps the dict alive, so the id cannot be recycled
+    path = weights or os.environ.get("DF3D_B200_WEIGHTS")
+    if path:
+        st = os.stat(path)
+        return ("file", os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    return ("random", 0)
+
+
+def get_engine(state_dict, in_h, in_w, max_batch, device="cuda", mean=(0.5, 0.5, 0.5), weights=None):
+    """The cached engine for these weights / input size / mean, rebuilt when any of them changes or when a larger
+    batch is asked for.  The previous engine is closed first (LRU of one)."""
+    key = (_weights_key(state_dict, weights), int(in_h), int(in_w), str(device), tuple(mean))
+    with _ENGINE_LOCK:
+        eng = _ENGINE["engine"]
+        if eng is not None and _ENGINE["key"] == key and eng.max_batch >= max_batch:
+            return eng
+        if eng is not None:
+            eng.close()
+            _ENGINE.update(key=None, engine=None, ref=None)
+        sd = state_dict if state_dict is not None else load_state_dict(weights)
+        eng = HourglassEngine(sd, in_h, in_w, max_batch, device=device, mean=mean)
+        _ENGINE.update(key=key, engine=eng, ref=state_dict)
+        return eng
+
+
+def drop_engine():
+    with _ENGINE_LOCK:
+        if _ENGINE["engine"] is not None:
+            _ENGINE["engine"].close()
+        _ENGINE.update(key=None, engine=None, ref=None)
+
+
+_JPEG = {}
+
+
+def _jpeg_decoder():
+    from . import ops
+
+    dec = _JPEG.get("dec")
+    if dec is None:
+        dec = _JPEG["dec"] = ops.JpegDecoder()
+    return dec
 
 
 def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return_confidence=True, max_img_id=None,
                      batch_size=8, disable_pin_memory=False, state_dict=None, weights=None, input_size=None,
-                     device="cuda", gpu_decode=False):
-    """Runs the hourglass on every camera_{0..6}_img_{0..max_img_id}.jpg of `folder`."""
+                     device="cuda", gpu_decode=False, mean=None, block_frames=None, workers=None, stats=None):
+    """Runs the hourglass on every camera_{0..6}_img_{0..max_img_id}.jpg of `folder`.
+
+    batch_size is the reference's DataLoader batch (images per forward).  Here a forward runs over a block of
+    frames sized for the GPU (``block_frames_for``); a batch_size above that raises the block.  `stats`, when a
+    dict, receives the block plan and the seconds spent waiting for the host decode."""
+    from . import ops
+
     if max_img_id is None:
         raise ValueError("max_img_id is required")
+    if not torch.cuda.is_available():
+        raise RuntimeError("inference_folder needs a CUDA device (sm_100a); there is no CPU fallback")
     Hh, Wh = HEATMAP_SHAPE
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
-    dev_images = load_images(folder, max_img_id, (in_h, in_w), pin_memory=not disable_pin_memory, device=device,
-                             gpu_decode=gpu_decode)
-    sd = state_dict if state_dict is not None else load_state_dict(weights)
-    # batch_size is the reference's DataLoader batch; here the whole folder is one device batch and
-    # the engine chunks internally, so it only bounds the workspace for tiny folders
-    eng = get_engine(sd, in_h, in_w, max(NUM_CAMERAS * T, batch_size), device=device)
-    flip = torch.zeros((NUM_CAMERAS, T), dtype=torch.uint8)
-    for c in camera_ids_to_flip:
-        flip[int(c)] = 1
-    res = eng.forward(dev_images, flip=flip.reshape(-1).to(device), return_heatmap=return_heatmap)
-    idx, conf = res[0], res[1]
-    idx_h = idx.cpu().numpy().astype(np.int64).reshape(NUM_CAMERAS, T, -1)
+    bf = int(block_frames) if block_frames else block_frames_for(in_h, in_w, T, batch_size)
+    blocks = plan_blocks(T, bf)
+    dev = torch.device(device)
+    eng = get_engine(state_dict, in_h, in_w, NUM_CAMERAS * bf, device=device, mean=load_mean(mean), weights=weights)
+    K = eng.num_classes
     hh, hw = eng.heatmap_shape
+    flip_cam = torch.zeros(NUM_CAMERAS, dtype=torch.uint8)
+    for c in camera_ids_to_flip:
+        flip_cam[int(c)] = 1
+    idx_all = torch.empty((NUM_CAMERAS, T, K), dtype=torch.int32, device=dev)
+    conf_all = torch.empty((NUM_CAMERAS, T, K), dtype=torch.float32, device=dev)
+    heat_all = torch.empty((NUM_CAMERAS, T, K, hh, hw), dtype=torch.float32) if return_heatmap else None
+    import time
+
+    wait_s = 0.0
+    with torch.cuda.device(dev), FolderReader(folder, workers=workers) as rd:
+        main = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream()
+        if gpu_decode:
+            pending = rd.read_bytes_async(*blocks[0])
+        else:
+            Hs, Ws = rd.shape
+            host = [torch.empty((NUM_CAMERAS, bf, Hs, Ws), dtype=torch.uint8) for _ in range(2)]
+            if not disable_pin_memory:
+                host = [h.pin_memory() for h in host]
+            staged = [torch.empty((NUM_CAMERAS, bf, Hs, Ws), dtype=torch.uint8, device=dev) for _ in range(2)]
+            uploaded = [torch.cuda.Event() for _ in range(2)]   # H2D of the slot finished (host buffer reusable)
+            consumed = [torch.cuda.Event() for _ in range(2)]   # compute done with the device slot
+            for ev in consumed:
+                ev.record(main)
+            pending = rd.read_block_async(*blocks[0], host[0])
+        for k, (t0, t1) in enumerate(blocks):
+            tc = t1 - t0
+            slot = k & 1
+            t_w = time.perf_counter()
+            got = rd.wait(pending)                               # block k decoded (or its bytes read)
+            wait_s += time.perf_counter() - t_w
+            if gpu_decode:
+                if k + 1 < len(blocks):
+                    pending = rd.read_bytes_async(*blocks[k + 1])
+                native = _jpeg_decoder().decode_gray(got, device=dev)          # (7*tc, Hs, Ws), camera-major
+            else:
+                if k + 1 < len(blocks):
+                    if k >= 1:
+                        uploaded[slot ^ 1].synchronize()         # the other host buffer has left for the device
+                    pending = rd.read_block_async(*blocks[k + 1], host[slot ^ 1])
+                copy_stream.wait_event(consumed[slot])
+                with torch.cuda.stream(copy_stream):
+                    staged[slot][:, :tc].copy_(host[slot][:, :tc], non_blocking=True)
+                    uploaded[slot].record(copy_stream)
+                main.wait_event(uploaded[slot])
+                native = staged[slot][:, :tc].reshape(NUM_CAMERAS * tc, Hs, Ws) if tc == bf else \
+                    staged[slot][:, :tc].contiguous().reshape(NUM_CAMERAS * tc, Hs, Ws)
+            images = native if tuple(native.shape[1:]) == (in_h, in_w) else ops.resize_gray_u8(native, (in_h, in_w))
+            flip = flip_cam.view(NUM_CAMERAS, 1).expand(NUM_CAMERAS, tc).reshape(-1).to(dev)
+            res = eng.forward(images, flip=flip, return_heatmap=return_heatmap)
+            idx_all[:, t0:t1] = res[0].view(NUM_CAMERAS, tc, K)
+            conf_all[:, t0:t1] = res[1].view(NUM_CAMERAS, tc, K)
+            if not gpu_decode:
+                consumed[slot].record(main)
+            if return_heatmap:
+                heat_all[:, t0:t1] = res[2][..., :K].permute(0, 3, 1, 2).reshape(NUM_CAMERAS, tc, K, hh, hw).cpu()
+        idx_h = idx_all.cpu().numpy().astype(np.int64)
+        conf_h = conf_all.cpu().numpy()
+    if stats is not None:
+        stats.update(blocks=len(blocks), block_frames=bf, decode_wait_s=wait_s, workers=rd.workers)
     points2d = np.stack([(idx_h // hw) / hh, (idx_h % hw) / hw], axis=-1).astype(np.float64)
     out = [points2d]
     if return_heatmap:
-        K = eng.num_classes
-        out.append(res[2][..., :K].permute(0, 3, 1, 2).reshape(NUM_CAMERAS, T, K, hh, hw).cpu().numpy())
+        out.append(heat_all.numpy())
     if return_confidence:
-        out.append(conf.cpu().numpy().reshape(NUM_CAMERAS, T, -1, 1))
+        out.append(conf_h.reshape(NUM_CAMERAS, T, -1, 1))
     return tuple(out) if len(out) > 1 else out[0]

@@ -157,21 +157,20 @@ def _aligned_ptr(ws):
     return C.c_void_p(a), ws.numel() - (a - p)
 
 
-REPORT_FIELDS = ("cost0", "cost", "lambda", "iters", "accepted", "n_obs", "status")
-
-
 def _decode_report(rep_bytes):
     raw = rep_bytes.cpu().numpy().tobytes()
     r = _lib.BAReport.from_buffer_copy(raw)
-    return {"cost0": r.cost0, "cost": r.cost, "lambda": r.lambda_, "iters": r.iters,
+    return {"cost0": r.cost0, "cost": r.cost, "reg": r.reg, "iters": r.iters,
             "accepted": r.accepted, "n_obs": r.n_obs, "status": r.status}
 
 
-def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, lambda0=1e-6, workspace=None):
-    """In-place LM bundle adjustment.  cam_rt (C,6) and pts3d (T,J,3) are updated.
+def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e-8, gtol=1e-8, workspace=None):
+    """In-place bundle adjustment (SciPy's trust-region-reflective iteration, see csrc/bundle_adjust.cu).
+    cam_rt (C,6) and pts3d (T,J,3) are updated.
 
     Returns a uint8 CUDA tensor holding the df3d_ba_report (decode with ``ba_report``; reading it
-    synchronises)."""
+    synchronises).  Every reduction runs in a fixed order: the same inputs give the same bits, which is
+    what lets a frame-sharded multi-GPU run solve the gathered problem replicated (pipeline.py)."""
     _need_cuda(cam_rt, intr4, pts_xy, pts3d)
     for t in (cam_rt, intr4, pts_xy, pts3d):
         if t.dtype != torch.float64 or not t.is_contiguous():
@@ -179,46 +178,20 @@ def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, lambda0
     Cn, T, J, _ = pts_xy.shape
     ws = workspace if workspace is not None else ba_workspace(Cn, T, J, cam_rt.device)
     wp, wn = _aligned_ptr(ws)
-    opts = _lib.BAOpts(int(max_iters), float(ftol), float(lambda0))
+    opts = _lib.BAOpts(int(max_iters), float(ftol), float(xtol), float(gtol))
     rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
     check(lib.df3d_bundle_adjust(_ptr(cam_rt), _ptr(intr4), _ptr(pts_xy), Cn, T, J, C.byref(opts), _ptr(pts3d),
                                  _ptr(rep), wp, wn, _stream()))
     return rep
 
 
+def bundle_adjust_launches(max_iters):
+    opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8)
+    return int(lib.df3d_bundle_adjust_launches(C.byref(opts)))
+
+
 def ba_report(rep):
     return _decode_report(rep)
-
-
-def bundle_adjust_distributed(cam_rt, intr4, pts_xy, pts3d, group=None, max_iters=20, ftol=1e-4, lambda0=1e-6):
-    """Frame-sharded LM: every rank holds its own frames' observations / points and the replicated
-    cameras; the Schur-reduced camera system and the candidate cost are all-reduced (sum) over
-    `group` each iteration.  Produces the same iterates as the single-GPU solver on the
-    concatenated frames (up to summation order)."""
-    import torch.distributed as dist
-
-    _need_cuda(cam_rt, intr4, pts_xy, pts3d)
-    Cn, T, J, _ = pts_xy.shape
-    ws = ba_workspace(Cn, T, J, cam_rt.device)
-    wp, wn = _aligned_ptr(ws)
-    opts = _lib.BAOpts(int(max_iters), float(ftol), float(lambda0))
-    sysbuf = torch.zeros(lib.df3d_ba_system_doubles(Cn), dtype=torch.float64, device=cam_rt.device)
-    cost = torch.zeros(2, dtype=torch.float64, device=cam_rt.device)
-    rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
-    s = _stream()
-    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    check(lib.df3d_ba_begin(_ptr(cam_rt), C.byref(opts), Cn, T, J, wp, wn, s))
-    for _ in range(max_iters):
-        check(lib.df3d_ba_linearize(_ptr(intr4), _ptr(pts_xy), _ptr(pts3d), Cn, T, J, wp, _ptr(sysbuf), s))
-        if multi:
-            dist.all_reduce(sysbuf, group=group)
-        check(lib.df3d_ba_solve(Cn, wp, _ptr(sysbuf), s))
-        check(lib.df3d_ba_evaluate(_ptr(intr4), _ptr(pts_xy), _ptr(pts3d), Cn, T, J, wp, _ptr(cost), s))
-        if multi:
-            dist.all_reduce(cost, group=group)
-        check(lib.df3d_ba_decide(Cn, T, J, wp, _ptr(cost), _ptr(pts3d), s))
-    check(lib.df3d_ba_end(_ptr(cam_rt), Cn, wp, _ptr(rep), s))
-    return rep
 
 
 def reprojection_error(cam_rt, intr4, pts_xy, pts3d):

@@ -3,9 +3,13 @@ DLT -> bundle adjustment -> DLT, everything enqueued on one CUDA stream with no 
 
 This is what ``Core.pose2d_estimation`` + ``Core.calibrate_calc`` + ``Core.save`` run in the
 reference (df3d/core.py:170-203, 229-250, 351-360) minus file I/O, and what bench.py times.
-Frames shard across ranks (``run_sharded``): every stage is per-frame except bundle adjustment,
-whose Schur-reduced camera system is all-reduced each iteration, and the final all-gather of the
-3-D joints.
+
+Multi-GPU (one process per GPU, ``group`` = the NCCL process group): frames shard in contiguous blocks, all
+7 cameras of a frame on one rank.  Hourglass, arg-max, packing and DLT need no communication.  Bundle
+adjustment is ONE global problem over all frames (42 shared camera unknowns): the packed 2-D
+points of the frames it uses (4 256 B / frame) are all-gathered, every rank solves the same problem with the
+same bit-reproducible kernels and ends with identical cameras -- no collective inside the solver -- then
+triangulates its own frames; one all-gather of the 3-D joints (912 B / frame) ends the step.
 """
 import numpy as np
 import torch
@@ -36,7 +40,7 @@ def reorder_calib(calib, camera_ordering):
 
 class Pose3DPipeline:
     def __init__(self, state_dict, in_h, in_w, max_images, image_shape, camera_ordering=range(7), calib=None,
-                 device="cuda", mean=0.5, ba_max_iters=10, ba_ftol=1e-4):
+                 device="cuda", mean=0.5, ba_max_iters=10, ba_ftol=1e-4, ba_max_frames=None):
         self.device = torch.device(device)
         self.engine = HourglassEngine(state_dict, in_h, in_w, max_images, device=device, mean=mean)
         self.order = [int(c) for c in camera_ordering]
@@ -46,7 +50,7 @@ class Pose3DPipeline:
         cam_rt = np.stack([np.concatenate([rodrigues_vec(calib["R"][c]), calib["tvec"][c]]) for c in range(NUM_CAMERAS)])
         self.cam_rt0 = torch.as_tensor(cam_rt, device=self.device)
         self.intr4 = torch.as_tensor(intr_to_vec4(calib["intr"]), device=self.device)
-        self.ba_max_iters, self.ba_ftol = ba_max_iters, ba_ftol
+        self.ba_max_iters, self.ba_ftol, self.ba_max_frames = ba_max_iters, ba_ftol, ba_max_frames
         self._flip_cache = {}
         self._ba_ws = {}
 
@@ -65,22 +69,32 @@ class Pose3DPipeline:
         p2d, pxy = ops.pack_points2d(idx, NUM_CAMERAS, T, self.engine.heatmap_shape, self.order, self.image_shape)
         return idx, conf, p2d, pxy
 
+    def ba_frame_subset(self, T_total):
+        """Indices of the frames the bundle adjustment uses: all of them (what the reference does), or a strided
+        subset of at most `ba_max_frames` (100 000 frames, BA on <= 1 000)."""
+        if self.ba_max_frames is None or T_total <= self.ba_max_frames:
+            return None
+        stride = -(-T_total // self.ba_max_frames)
+        return torch.arange(0, T_total, stride, device=self.device)
+
     def pose3d(self, pxy, group=None):
-        """pts_xy (7,T,J,2) -> cameras after BA (7,6), points3d (T,J,3) re-triangulated (core.py:355)."""
+        """pts_xy (7,T,J,2) of this rank's frames -> cameras after BA (7,6), R (7,3,3), points3d (T,J,3)
+        re-triangulated with the new cameras (core.py:355), BA report."""
         Cn, T, J, _ = pxy.shape
         cam = self.cam_rt0.clone()
+        ba_xy = gather_frames(pxy, group, dim=1) if group is not None else pxy   # every rank: all frames' 2-D points
+        sel = self.ba_frame_subset(ba_xy.shape[1])
+        if sel is not None:
+            ba_xy = ba_xy.index_select(1, sel).contiguous()
         P0, _ = ops.projection_matrices(cam, self.intr4)
-        X = ops.triangulate_dlt(P0, pxy)
-        if group is not None:
-            rep = ops.bundle_adjust_distributed(cam, self.intr4, pxy, X, group=group, max_iters=self.ba_max_iters, ftol=self.ba_ftol)
-        else:
-            key = (Cn, T, J)
-            if key not in self._ba_ws:
-                self._ba_ws[key] = ops.ba_workspace(Cn, T, J, self.device)
-            rep = ops.bundle_adjust(cam, self.intr4, pxy, X, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
-                                    workspace=self._ba_ws[key])
+        X = ops.triangulate_dlt(P0, ba_xy)
+        key = (Cn, ba_xy.shape[1], J)
+        if key not in self._ba_ws:
+            self._ba_ws[key] = ops.ba_workspace(*key, self.device)
+        rep = ops.bundle_adjust(cam, self.intr4, ba_xy, X, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
+                                workspace=self._ba_ws[key])
         P1, R1 = ops.projection_matrices(cam, self.intr4)
-        X1 = ops.triangulate_dlt(P1, pxy)
+        X1 = ops.triangulate_dlt(P1, pxy)                        # own frames only
         return cam, R1, X1, rep
 
     def run(self, images, T, group=None):
@@ -91,20 +105,28 @@ class Pose3DPipeline:
 
     def launches(self, n_images):
         """Kernel launches of one `run` (for bench.py's gpu_launches): hourglass plan + pack + 2 x
-        (projection + DLT) + BA (begin + max_iters x 5 + end)."""
-        return self.engine.launches(n_images) + 1 + 4 + (2 + 5 * self.ba_max_iters)
+        (projection + DLT) + bundle adjustment."""
+        return self.engine.launches(n_images) + 1 + 4 + ops.bundle_adjust_launches(self.ba_max_iters)
 
 
-def gather_frames(x, group=None):
-    """Single all-gather of a per-rank (T_local, ...) tensor along the frame axis (NCCL over NVLink
-    on the GPU box, gloo in the CPU tests)."""
+def gather_frames(x, group=None, dim=0):
+    """Single all-gather of a per-rank tensor along its frame axis `dim` (NCCL over NVLink on the GPU box,
+    gloo in the CPU tests).  Every rank must hold the same number of frames."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return x
-    parts = [torch.empty_like(x) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(parts, x.contiguous(), group=group)
-    return torch.cat(parts, dim=0)
+    world = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x, group=group)          # concatenation along dim 0, rank-major
+    if dim == 0:
+        return out
+    # (world, ..., T, ...) -> (..., world * T, ...): rank-major along the frame axis
+    out = out.reshape((world,) + tuple(x.shape)).movedim(0, dim)
+    shape = list(x.shape)
+    shape[dim] *= world
+    return out.reshape(shape).contiguous()
 
 
 def shard_frames(T, rank, world):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DF3D_ABI_VERSION 1
+#define DF3D_ABI_VERSION 2
 
 enum {
   DF3D_OK = 0,
@@ -120,24 +120,29 @@ int df3d_projection_matrices(const double* cam_rt_dev, const double* intr_dev, i
 /* --------------------------------------------------------------------------------------------
  * Bundle adjustment of the C camera extrinsics + all 3-D points.  Replaces pyba
  * CameraNetwork.bundle_adjust(update_intrinsic=False, update_distort=False)
- * (call site df3d/core.py:249).  Levenberg-Marquardt on the Schur-reduced camera system,
- * column-norm (Jacobi) scaled like SciPy's x_scale='jac', analytic Jacobian, fp64.
- * Cameras without observations are returned unchanged.
+ * (call site df3d/core.py:249), i.e. scipy.optimize.least_squares(method='trf', x_scale='jac',
+ * ftol=1e-4) on the re-projection residuals.  The gauge is free, so the result depends on the
+ * step rule: the kernels follow SciPy's trf_no_bounds (tr_solver='lsmr') iteration -- Jacobi
+ * column scaling with a running maximum, Cauchy-step regularisation, 2-D subspace trust-region
+ * step, ratio test / radius update / ftol-xtol-gtol termination -- with the regularised
+ * Gauss-Newton step solved exactly through the Schur complement on the 6C camera unknowns
+ * (analytic Jacobian, fp64).  Cameras without observations are returned unchanged.
  * ------------------------------------------------------------------------------------------ */
 typedef struct df3d_ba_opts {
-  int max_iters;      /* LM iterations (accepted + rejected); reference converges in 3-4 */
-  double ftol;        /* stop when dF < ftol * F  (reference: 1e-4)                       */
-  double lambda0;     /* initial damping in the Jacobi-scaled space (default 1e-6)        */
+  int max_iters;      /* candidate steps evaluated (SciPy: nfev - 1); the reference needs 3-4 */
+  double ftol;        /* stop when dF < ftol * F and ratio > 0.25  (reference: 1e-4)          */
+  double xtol;        /* stop when |dx| < xtol * (xtol + |x|)      (SciPy default 1e-8)       */
+  double gtol;        /* stop when |g|_inf < gtol                  (SciPy default 1e-8)       */
 } df3d_ba_opts;
 
 typedef struct df3d_ba_report {   /* written to DEVICE memory (no host sync) */
   double cost0;       /* 0.5 * sum r^2 at entry */
   double cost;        /* at exit                */
-  double lambda;      /* final damping          */
-  int32_t iters;      /* linearisations done    */
-  int32_t accepted;   /* accepted steps         */
-  int32_t n_obs;      /* observations used      */
-  int32_t status;     /* 1 = ftol reached, 0 = max_iters */
+  double reg;         /* last regularisation of the Gauss-Newton step (Jacobi-scaled space) */
+  int32_t iters;      /* candidate steps evaluated */
+  int32_t accepted;   /* accepted steps            */
+  int32_t n_obs;      /* observations used         */
+  int32_t status;     /* SciPy's codes: 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol, 0 max_iters */
 } df3d_ba_report;
 
 size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J);
@@ -146,28 +151,16 @@ size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J);
  *   intr_dev   : (C,4) fx,fy,cx,cy
  *   pts_xy_dev : (C,T,J,2) pixel (x,y), visibility rule as in df3d_triangulate_dlt
  *   pts3d_dev  : (T,J,3) in: initial points (DLT with the initial cameras), out: BA points
- *   report_dev : df3d_ba_report in device memory (may be NULL)                              */
+ *   report_dev : df3d_ba_report in device memory (may be NULL)
+ * Fixed launch sequence (2 + 6 * max_iters kernels, no host synchronisation); every reduction runs in a
+ * fixed order, so the result is bit-reproducible -- frame-sharded multi-GPU runs all-gather the 2-D points and
+ * run this solver replicated, every rank ends with identical cameras. */
 int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double* pts_xy_dev,
                        int C, int T, int J, const df3d_ba_opts* opts, double* pts3d_dev,
                        df3d_ba_report* report_dev, void* workspace_dev, size_t workspace_bytes,
                        void* stream);
-
-/* Stepwise form of the same solver for frame-sharded multi-GPU runs: the caller all-reduces
- * (sum) `sys_dev` (df3d_ba_system_doubles() float64) across ranks between _linearize and
- * _solve, and `cost_dev` (2 float64: candidate cost, unused) between _evaluate and _decide.
- * With one rank this is exactly what df3d_bundle_adjust runs internally. */
-size_t df3d_ba_system_doubles(int C);
-int df3d_ba_begin(const double* cam_rt_dev, const df3d_ba_opts* opts, int C, int T, int J,
-                  void* workspace_dev, size_t workspace_bytes, void* stream);
-int df3d_ba_linearize(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
-                      int C, int T, int J, void* workspace_dev, double* sys_dev, void* stream);
-int df3d_ba_solve(int C, void* workspace_dev, const double* sys_dev, void* stream);
-int df3d_ba_evaluate(const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
-                     int C, int T, int J, void* workspace_dev, double* cost_dev, void* stream);
-int df3d_ba_decide(int C, int T, int J, void* workspace_dev, const double* cost_dev,
-                   double* pts3d_dev, void* stream);
-int df3d_ba_end(double* cam_rt_dev, int C, void* workspace_dev, df3d_ba_report* report_dev,
-                void* stream);
+/* kernels one df3d_bundle_adjust call launches (for bench.py's gpu_launches) */
+int df3d_bundle_adjust_launches(const df3d_ba_opts* opts);
 
 /* Mean L2 reprojection error in pixels (pyba CameraNetwork.reprojection_error(), printed at
  * df3d/core.py:250).  out_dev: 2 float64 = {sum of distances, number of observations}. */

@@ -26,7 +26,7 @@ def test_python_binding_covers_header(lib_built):
     from deepfly3d_b200 import _lib
 
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib.df3d_abi_version() == 1
+    assert _lib.lib.df3d_abi_version() == 2
 
 
 def test_argument_validation_without_gpu(lib_built):
@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu(lib_built):
     d_bad = _lib.HGDesc(8, 19, 250, 256, 4)
     assert lib.df3d_hg_param_count(ctypes.byref(d_bad)) == 0
     assert lib.df3d_bundle_adjust_workspace_bytes(7, 15, 38) > 0
-    assert lib.df3d_ba_system_doubles(7) == 2102
+    assert lib.df3d_bundle_adjust_launches(None) == 2 + 6 * 20
 
 
 def test_flatten_matches_param_count(lib_built):

@@ -1,9 +1,9 @@
 """Host-side logic of the frame-sharded multi-GPU path on CPU: world_size 2, gloo backend.
 
-The data path has exactly two exchange points (multi-GPU): the all-reduce of the
-Schur-reduced camera system inside bundle adjustment and ONE all-gather of the 3-D joints.  Here
-the sharding arithmetic and the gather (frame order, ragged last shard handled by the caller) run
-with gloo; the same code runs with NCCL on the GPU box."""
+The data path has exactly two exchange points (multi-GPU): the all-gather of the packed 2-D
+points that feeds the replicated bundle adjustment (frame axis = dim 1 of (7, T, 38, 2)) and ONE
+all-gather of the 3-D joints (frame axis = dim 0).  Here the sharding arithmetic and both gathers
+(frame order preserved rank-major) run with gloo; the same code runs with NCCL on the GPU box."""
 import os
 import socket
 
@@ -32,10 +32,10 @@ def _worker(rank, world, port, T, out_dir):
     full = torch.arange(T * 38 * 3, dtype=torch.float64).reshape(T, 38, 3)
     local = full[lo:hi].clone()
     gathered = gather_frames(local)
-    # the reduced camera system is additive over frame shards: emulate the all-reduce
-    sysbuf = torch.full((2102,), float(hi - lo), dtype=torch.float64)
-    dist.all_reduce(sysbuf)
-    torch.save({"gathered": gathered, "sys": sysbuf, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
+    # the 2-D points of every rank's frames, gathered along the frame axis of (7, T, 38, 2)
+    full2d = torch.arange(7 * T * 38 * 2, dtype=torch.float64).reshape(7, T, 38, 2)
+    gathered2d = gather_frames(full2d[:, lo:hi].contiguous(), dim=1)
+    torch.save({"gathered": gathered, "gathered2d": gathered2d, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -47,7 +47,7 @@ def test_shard_and_gather_two_ranks(tmp_path):
     for r in range(world):
         d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert torch.equal(d["gathered"], full)          # frame order preserved on every rank
-        assert float(d["sys"][0]) == T                   # sum over shards == whole problem
+        assert torch.equal(d["gathered2d"], torch.arange(7 * T * 38 * 2, dtype=torch.float64).reshape(7, T, 38, 2))
         ranges.append(d["range"])
     assert ranges == [(0, 32), (32, 64)]
 

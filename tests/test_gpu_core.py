@@ -131,3 +131,95 @@ def test_pipeline_matches_stagewise(golden):
     assert torch.equal(out["idx"], idx) and torch.equal(out["points2d"], p2d) and torch.equal(out["pts_xy"], pxy)
     assert out["points3d_wo_procrustes"].shape == (T, 38, 3) and torch.isfinite(out["points3d_wo_procrustes"]).all()
     assert pipe.launches(7 * T) > 100
+
+
+def test_inference_folder_streams_blocks_and_loads_checkpoint(working, tmp_path):
+    """The streaming loader (blocks of frames, threaded decode, copy stream) gives the same result whatever the
+    block size; `weights=` takes a file with the layout of df2d's sh8_deepfly.tar ({'state_dict': {'module.*'}}) and
+    `mean=` a mean.pth.tar (reference df3d/config.py:30-39); a second call with OTHER weights must not be served
+    by the cached engine of the first."""
+    from deepfly3d_b200 import inference
+
+    model_a, model_b = ohg.make_model(2, seed=0), ohg.make_model(2, seed=9)
+    wa, wb = tmp_path / "a.tar", tmp_path / "b.tar"
+    torch.save({"state_dict": {"module." + k: v for k, v in model_a.state_dict().items()}, "epoch": 1}, wa)
+    torch.save({"state_dict": {"module." + k: v for k, v in model_b.state_dict().items()}, "epoch": 1}, wb)
+    torch.save({"mean": torch.tensor([0.22, 0.22, 0.22])}, tmp_path / "mean.pth.tar")
+    kw = dict(folder=working, camera_ids_to_flip=[4, 5, 6], max_img_id=2, mean=str(tmp_path / "mean.pth.tar"))
+    stats = {}
+    p_a, c_a = inference.inference_folder(weights=str(wa), stats=stats, **kw)
+    assert stats["blocks"] == 1 and p_a.shape == (7, 3, 19, 2) and c_a.shape == (7, 3, 19, 1)
+    p_a2, c_a2 = inference.inference_folder(weights=str(wa), block_frames=2, stats=stats, **kw)     # blocks (0,2), (2,3)
+    assert stats["blocks"] == 2
+    assert np.array_equal(p_a, p_a2) and np.array_equal(c_a, c_a2)
+    p_sd, c_sd = inference.inference_folder(state_dict=model_a.state_dict(), **kw)                  # same weights as a dict
+    assert np.array_equal(p_a, p_sd) and np.array_equal(c_a, c_sd)
+    p_b, c_b = inference.inference_folder(weights=str(wb), **kw)
+    assert not np.array_equal(c_a, c_b), "second checkpoint was served by the first one's engine"
+    p_m, c_m = inference.inference_folder(weights=str(wa), **{**kw, "mean": 0.5})
+    assert not np.array_equal(c_a, c_m), "the mean file was ignored"
+    # against the oracle with that mean
+    import cv2
+
+    imgs = np.stack([[cv2.resize(cv2.imread(os.path.join(working, f"camera_{c}_img_{t}.jpg"), cv2.IMREAD_GRAYSCALE),
+                                 (512, 256), interpolation=cv2.INTER_LINEAR) for t in range(3)] for c in range(7)])
+    flip = np.zeros((7, 3), dtype=bool)
+    flip[4:] = True
+    with torch.no_grad():
+        x = ohg.preprocess_u8(torch.as_tensor(imgs.reshape(21, 256, 512)), flip=flip.reshape(-1), mean=0.22)
+        heat = model_a(x, emulate_bf16=True)[-1]
+    _, conf = oargmax.heatmap_argmax(heat.numpy())
+    rngv = float(heat.max() - heat.min())
+    assert np.abs(c_a.reshape(21, 19) - conf).max() < 0.01 * rngv
+    inference.drop_engine()
+
+
+def _sharded_worker(rank, world, port, T, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from deepfly3d_b200.inference import random_state_dict
+    from deepfly3d_b200.pipeline import Pose3DPipeline, gather_frames, shard_frames
+
+    full = ohg.to_uint8(ohg.synthetic_images(7 * T, 128, 128, seed=5)).view(7, T, 128, 128)
+    lo, hi = shard_frames(T, rank, world)
+    pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * (hi - lo), image_shape=[960, 480], device=f"cuda:{rank}")
+    out = pipe.run(full[:, lo:hi].reshape(7 * (hi - lo), 128, 128).cuda(), hi - lo, group=dist.group.WORLD)
+    x3d = gather_frames(out["points3d_wo_procrustes"], dist.group.WORLD)
+    torch.cuda.synchronize()
+    torch.save({"x3d": x3d.cpu(), "cam": out["cam_rt"].cpu(), "idx": out["idx"].cpu(), "range": (lo, hi)},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_sharded_two_gpus_equals_single_gpu(tmp_path, lib_built):
+    """Frame-sharded run over NCCL (2 ranks: all-gather of the 2-D points, replicated bundle adjustment, local
+    DLT, all-gather of the 3-D joints) == the single-GPU run on the concatenated frames, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+
+    import torch.multiprocessing as mp
+
+    from deepfly3d_b200.inference import random_state_dict
+    from deepfly3d_b200.pipeline import Pose3DPipeline
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    T = 12
+    mp.spawn(_sharded_worker, args=(2, port, T, str(tmp_path)), nprocs=2, join=True)
+    full = ohg.to_uint8(ohg.synthetic_images(7 * T, 128, 128, seed=5))
+    pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * T, image_shape=[960, 480])
+    ref = pipe.run(full.cuda(), T)
+    torch.cuda.synchronize()
+    for r in range(2):
+        d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        lo, hi = d["range"]
+        assert torch.equal(d["idx"], ref["idx"].cpu().view(7, T, -1)[:, lo:hi].reshape(7 * (hi - lo), -1))
+        assert torch.equal(d["cam"], ref["cam_rt"].cpu()), "replicated bundle adjustment differs from the single-GPU solve"
+        assert torch.equal(d["x3d"], ref["points3d_wo_procrustes"].cpu())

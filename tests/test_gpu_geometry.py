@@ -143,22 +143,60 @@ def _run_ba(ops, calib, pts_xy, **kw):
 
 
 def test_bundle_adjust_golden(ops, golden):
-    """Same input as the reference's test_calibration; north-star tolerance: 1e-3 mm on 3-D joints."""
+    """Same input as the reference's test_calibration (tests/test_df3d.py:198-244).  North-star tolerance:
+    1e-3 mm on the 3-D joints; measured 5e-5 (the distance between SciPy's truncated LSMR step, which
+    produced the golden file, and the exact regularised Gauss-Newton step -- tools/ba_proto.py)."""
     r3 = golden["result_3d"]
     pts_xy = g.to_pixels_xy(golden["result_2d"]["points2d"], [960, 480])
     cam, R1, X1, rep, err, cam0 = _run_ba(ops, golden["calib"], pts_xy)
     assert rep["n_obs"] == 1590
     assert abs(rep["cost0"] - 11953.29) < 0.05 and abs(rep["cost"] - 11136.13) < 0.05   # SciPy: 11953.29 -> 11136.13
-    assert rep["status"] == 1 and rep["accepted"] <= 6
-    assert np.abs(X1 - r3["points3d_wo_procrustes"]).max() < 1e-3
-    assert np.abs(R1 - r3["R"]).max() < 1e-3
+    # SciPy's trace on this input (SURVEY.md App. B step 8): 3 accepted steps, 4 function evaluations, ftol
+    assert rep["status"] == 2 and rep["accepted"] == 3 and rep["iters"] == 3
+    dX = np.abs(X1 - r3["points3d_wo_procrustes"]).max()
+    print(f"golden: max |X - X_golden| = {dX:.3e}")
+    assert dX < 1e-4
+    assert np.abs(R1 - r3["R"]).max() < 1e-4            # reference test: atol 1e-4 on the camera parameters
+    assert np.abs(cam[:, 3:] - r3["tvec"]).max() < 2e-3
     assert abs(err - 2.942) < 5e-3
     # camera 3 has no observations: returned bit-identical
     assert np.array_equal(cam[3], cam0[3])
 
 
-def test_bundle_adjust_vs_oracle_synthetic(ops, golden):
-    """Perturbed cameras, synthetic skeleton, 40 frames: GPU LM vs the SciPy-TRF oracle."""
+def _oracle_ba(calib, pts):
+    Ro, to, sol = g.bundle_adjust(calib["R"], calib["tvec"], calib["intr"], pts, return_info=True)
+    Xo = g.triangulate_dlt(g.projection_matrices(Ro, to, calib["intr"]), pts)
+    return Ro, to, Xo, sol
+
+
+@pytest.mark.parametrize("T", [40, 256, 1000])
+def test_bundle_adjust_vs_scipy_config3(ops, T):
+    """BASELINE.json configs[2] geometry (perturbed true cameras, jittered template
+    skeleton, observations quantised to the 64 x 128 heat-map grid; BA starts from the packaged calibration):
+    GPU bundle adjustment + DLT against the SciPy-TRF oracle at the sizes the bench runs (256 and 1 000 frames).
+    Tolerance: north-star 1e-3 mm on the 3-D joints; asserted 1e-4 (measured ~2e-5)."""
+    from oracle import synth
+
+    calib, pts, _ = synth.config3_geometry(T, seed=2)
+    cam, R1, X1, rep, err, _ = _run_ba(ops, calib, pts)
+    Ro, to, Xo, sol = _oracle_ba(calib, pts)
+    erro = g.reprojection_error(Ro, to, calib["intr"], pts, Xo)
+    dX = np.abs(X1 - Xo).max()
+    print(f"T={T}: max |X_gpu - X_scipy| = {dX:.3e}, cameras dR {np.abs(R1 - Ro).max():.2e} dt {np.abs(cam[:, 3:] - to).max():.2e}, "
+          f"cost {rep['cost']:.4f} vs {sol.cost:.4f}, evaluations {rep['iters']} vs {sol.nfev - 1}")
+    assert rep["status"] == sol.status and rep["iters"] == sol.nfev - 1     # same path through the trust-region loop
+    assert abs(rep["cost"] - sol.cost) < 1e-6 * sol.cost
+    assert abs(err - erro) < 1e-4 * erro
+    assert dX < 1e-4
+    assert np.abs(R1 - Ro).max() < 1e-4 and np.abs(cam[:, 3:] - to).max() < 5e-3
+    active = [c for c in range(7) if c != 3]
+    assert np.array_equal(cam[3, 3:], calib["tvec"][3])                     # no observations: untouched
+    assert np.all(np.abs(cam[active, 3:] - calib["tvec"][active]).max(axis=1) > 1e-3)
+
+
+def test_bundle_adjust_vs_oracle_noisy_views(ops, golden):
+    """Round-1 case kept, tightened from 1e-2 to the north-star 1e-3 (asserted 1e-4): perturbed start, unquantised
+    observations with 1 px Gaussian noise, 40 frames."""
     rng = np.random.default_rng(5)
     c = golden["calib"]
     T, J = 40, 38
@@ -175,30 +213,58 @@ def test_bundle_adjust_vs_oracle_synthetic(ops, golden):
         calib["R"][k] = g.rodrigues(g.rodrigues_inv(c["R"][k]) + rng.normal(scale=0.005, size=3))
         calib["tvec"][k] = c["tvec"][k] + rng.normal(scale=0.2, size=3)
     cam, R1, X1, rep, err, _ = _run_ba(ops, calib, pts)
-    Ro, to = g.bundle_adjust(calib["R"], calib["tvec"], calib["intr"], pts)
-    Xo = g.triangulate_dlt(g.projection_matrices(Ro, to, calib["intr"]), pts)
+    Ro, to, Xo, sol = _oracle_ba(calib, pts)
     erro = g.reprojection_error(Ro, to, calib["intr"], pts, Xo)
-    assert rep["status"] == 1
-    assert abs(err - erro) < 2e-3 * erro           # same optimum
-    assert np.abs(X1 - Xo).max() < 1e-2            # gauge freedom: looser than on the golden case
+    assert rep["status"] == sol.status
+    assert abs(err - erro) < 1e-4 * erro
+    dX = np.abs(X1 - Xo).max()
+    print(f"noisy views: max |X_gpu - X_scipy| = {dX:.3e}")
+    assert dX < 1e-4
 
 
-def test_bundle_adjust_stepwise_equals_monolithic(ops, golden):
-    from deepfly3d_b200.ops import intr_to_vec4
-
-    pts_xy = g.to_pixels_xy(golden["result_2d"]["points2d"], [960, 480])
+def test_bundle_adjust_ragged_and_single_view_points(ops, golden):
+    """Points seen by 0, 1, 2 ... 6 cameras (a 1-view point enters the residuals at X = 0, like in pyba) and a
+    frame count that does not fill the last block: same result as the oracle."""
+    rng = np.random.default_rng(6)
     c = golden["calib"]
-    cam0 = np.stack([np.concatenate([g.rodrigues_inv(c["R"][k]), c["tvec"][k]]) for k in range(7)])
-    intr4 = _cuda(intr_to_vec4(c["intr"]))
-    pxy = _cuda(pts_xy)
+    T, J = 23, 38
+    tmpl = golden["template"]["points3d"]
+    X = tmpl[rng.integers(0, tmpl.shape[0], size=T)] + rng.normal(scale=0.05, size=(T, J, 3))
+    pts = np.stack([g.project(X.reshape(-1, 3), c["R"][k], c["tvec"][k], c["intr"][k]) for k in range(7)]).reshape(7, T, J, 2)
+    pts += rng.normal(scale=1.0, size=pts.shape)
+    pts[rng.random((7, T, J)) < 0.5] = 0.0
+    pts[3] = 0.0
+    n_views = g.visibility(pts).sum(0)
+    assert (n_views == 0).any() and (n_views == 1).any() and (n_views >= 4).any()
+    cam, R1, X1, rep, err, _ = _run_ba(ops, c, pts)
+    Ro, to, Xo, sol = _oracle_ba(c, pts)
+    assert rep["n_obs"] == int(g.visibility(pts).sum())
+    assert abs(rep["cost"] - sol.cost) < 1e-5 * sol.cost
+    assert np.abs(X1 - Xo).max() < 1e-3
+
+
+def test_bundle_adjust_is_bit_reproducible(ops):
+    """Fixed-order reductions: two runs give the same bits (what the replicated multi-GPU solve relies on),
+    and a caller-provided workspace that held another problem before does not leak into the result."""
+    from deepfly3d_b200.ops import intr_to_vec4
+    from oracle import synth
+
+    calib, pts, _ = synth.config3_geometry(64, seed=3)
+    cam0 = np.stack([np.concatenate([g.rodrigues_inv(calib["R"][k]), calib["tvec"][k]]) for k in range(7)])
+    intr4 = _cuda(intr_to_vec4(calib["intr"]))
+    pxy = _cuda(pts)
+    ws = ops.ba_workspace(7, 64, 38, pxy.device)
     outs = []
-    for fn in (ops.bundle_adjust, ops.bundle_adjust_distributed):
+    for i in range(3):
         cam = _cuda(cam0)
         P0, _ = ops.projection_matrices(cam, intr4)
         X = ops.triangulate_dlt(P0, pxy)
-        fn(cam, intr4, pxy, X)
+        if i == 2:
+            ws.fill_(0xA5)
+        ops.bundle_adjust(cam, intr4, pxy, X, workspace=ws if i else None)
         outs.append((cam.cpu().numpy(), X.cpu().numpy()))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
 
 
 def test_errors_are_reported(ops):

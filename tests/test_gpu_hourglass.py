@@ -2,13 +2,19 @@
 bf16-emulating CPU oracle on seeded weights and inputs.
 
 Parity for this half is UNPINNED w.r.t. the reference (no pretrained weights, see
-oracle/hourglass.py); what is pinned here is kernel == oracle arithmetic.  Both sides round at the
-same points, so the only difference is the fp32 summation order inside a convolution, which can
-flip a bf16 rounding now and then.  Tolerances: heat-map within 2% of its dynamic range, arg-max
-index identical wherever the oracle's peak is separated from the runner-up by more than that
-noise, confidence within the same bound.  With seeded random weights the maps are noise-like, so
-many peaks are near ties (overall agreement is printed, not asserted tightly).  The reference's
-own test demands +-1 heat-map row (tests/test_df3d.py:171: atol=0.02).
+oracle/hourglass.py); what is pinned here is kernel == oracle arithmetic, against TWO oracles:
+  * the bf16-emulating oracle rounds where the kernels round, so the only difference is the fp32 summation
+    order inside a convolution, which can flip a bf16 rounding now and then: heat-map within 1 % of its
+    dynamic range, arg-max identical wherever the oracle's peak is separated from the runner-up by more than
+    that noise, confidence within the same bound;
+  * the plain fp32 oracle -- no bf16, and the inter-stack re-injection x + fc_(y) + score_(score(y)) evaluated
+    as the three separate convolutions of the published network, NOT the merged form the kernels (and the
+    emulating oracle) use: a wrong merge formula or a misplaced rounding point would show here.  Bound: 2.5 % of
+    the range (bf16 activations through up to 378 convolutions; the emulating oracle itself sits 0.6-0.75 %
+    from fp32); the arg-max mismatch rate against fp32 is printed (hard part 2).
+With seeded random weights the maps are noise-like, so many peaks are near ties; test_trained_network_*
+below repeats the comparison on a network that was trained to produce peaked maps.  The reference's own test
+demands +-1 heat-map row (tests/test_df3d.py:171: atol=0.02).
 """
 import numpy as np
 import pytest
@@ -42,10 +48,18 @@ def _compare(hgmod, stacks, H, W, B, seed, flip=None, float_input=False):
     torch.cuda.synchronize()
     with torch.no_grad():
         ref = model(x, emulate_bf16=True, gray_fold=not float_input)[-1]   # (B,K,Hh,Wh) fp32
+        ref32 = model(x)[-1]                                               # fp32 everywhere, unmerged re-injection
     got = heat[..., :19].permute(0, 3, 1, 2).cpu()
     assert torch.isfinite(got).all()
     rng_ = (ref.max() - ref.min()).item()
     err = (got - ref).abs().max().item() / rng_
+    err32 = (got - ref32).abs().max().item() / (ref32.max() - ref32.min()).item()
+    idx32, _ = oargmax.heatmap_argmax(ref32.numpy())
+    mis32 = float((idx.cpu().numpy() != idx32).mean())
+    d32 = np.abs(np.stack(np.divmod(idx.cpu().numpy(), W // 4)) - np.stack(np.divmod(idx32, W // 4))).max(axis=0)
+    print(f"  vs fp32 unmerged oracle: heat err {err32:.4f} of range, arg-max mismatch rate {mis32:.3f} "
+          f"({float((d32 > 1).mean()):.3f} by more than one pixel)")
+    assert err32 < 0.025, f"heat-map deviates from the fp32 (unmerged) oracle: {err32}"
     ref_idx, ref_conf = oargmax.heatmap_argmax(ref.numpy())
     # decode of the kernel's own heat-map must be bit-exact (integer index, fp32 peak)
     own_idx, own_conf = oargmax.heatmap_argmax(got.numpy())
@@ -72,7 +86,7 @@ def test_two_stack_reference_shape(hgmod):
     """config 1 shape: 2 stacks, 256 x 512 input -> 64 x 128 heat-map, mirrored cameras included."""
     err, agree, gap, cerr = _compare(hgmod, 2, 256, 512, 3, seed=0, flip=[False, True, True])
     print(f"2-stack 256x512: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
-    assert err < 0.02 and gap < 0.02 and cerr < 0.02
+    assert err < 0.01 and gap < 0.01 and cerr < 0.01
     assert agree > 0.7
 
 
@@ -80,14 +94,14 @@ def test_eight_stack_benchmark_shape(hgmod):
     """config 2 shape: 8 stacks, 256 x 256 input -> 64 x 64 heat-map."""
     err, agree, gap, cerr = _compare(hgmod, 8, 256, 256, 2, seed=1)
     print(f"8-stack 256x256: heat err {err:.4f} of range, arg-max agreement {agree:.3f}, worst gap {gap:.4f}")
-    assert err < 0.03 and gap < 0.03 and cerr < 0.03
+    assert err < 0.01 and gap < 0.01 and cerr < 0.01
     assert agree > 0.6
 
 
 def test_float_input_and_small_image(hgmod):
     """(B,3,H,W) float32 input path, smallest supported map sizes (64 x 64 input -> 1 x 1 at the bottom)."""
     err, agree, gap, cerr = _compare(hgmod, 2, 64, 64, 5, seed=2, float_input=True)
-    assert err < 0.02 and gap < 0.02
+    assert err < 0.01 and gap < 0.01
 
 
 def test_batch_larger_than_chunk_is_consistent(hgmod, monkeypatch):
