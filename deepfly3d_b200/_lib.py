@@ -47,6 +47,10 @@ SIGNATURES = {
     "df3d_bundle_adjust": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(BAOpts), _vp, _vp, _vp, _sz, _vp]),
     "df3d_bundle_adjust_launches": (_i, [C.POINTER(BAOpts)]),
     "df3d_reprojection_error": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "df3d_procrustes_workspace_bytes": (_sz, [_i]),
+    "df3d_procrustes": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "df3d_one_euro_filter": (_i, [_vp, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, _i, _vp, _vp]),
+    "df3d_smooth_pose2d": (_i, [_vp, _i, _i, _i, C.c_double, _vp, _vp]),
     "df3d_hg_param_count": (_sz, [C.POINTER(HGDesc)]),
     "df3d_hg_workspace_bytes": (_sz, [C.POINTER(HGDesc)]),
     "df3d_hg_create": (_i, [C.POINTER(HGDesc), _vp, _sz, C.POINTER(_vp)]),

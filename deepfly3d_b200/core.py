@@ -16,7 +16,6 @@ from typing import List, Optional
 
 import numpy as np
 
-from .procrustes import procrustes_seperate
 from .skeleton import HEATMAP_SHAPE, NUM_CAMERAS, NUM_JOINTS
 
 logger = logging.getLogger("df3d.logger")
@@ -194,8 +193,29 @@ class Core:
         print(f"Reprojection error is {self.camNet.reprojection_error()}")
 
     def get_points3d(self):
-        """(T,38,3) registered points (core.py:332-343 without the video-only rotation / One-Euro filter)."""
-        return procrustes_seperate(np.copy(self.camNet.points3d))
+        """(T,38,3) joints for display (core.py:332-343): procrustes registration, median-centring + axis swap
+        (df3d/plot_util.py:85-91, 10-17: y <- -z, z <- -y), One-Euro filter (df3d/signal_util.py:69-100)."""
+        import torch
+
+        from . import ops
+
+        pts = ops.procrustes(torch.as_tensor(np.ascontiguousarray(self.camNet.points3d, dtype=np.float64)).cuda())
+        p = pts.cpu().numpy()
+        p -= np.median(p.reshape(-1, 3), axis=0)
+        y, z = p[..., 1].copy(), p[..., 2].copy()
+        p[..., 1], p[..., 2] = -z, -y
+        return ops.one_euro_filter(torch.as_tensor(p).cuda()).cpu().numpy()
+
+    def smooth_points2d(self, cam_id, private_cache=dict()):
+        """Smoothed pixel tracks of one camera (core.py:286-296 -> df3d/signal_util.py:135-160)."""
+        import torch
+
+        from . import ops
+
+        if cam_id not in private_cache:
+            pts = torch.as_tensor(np.ascontiguousarray(self.camNet.cam_list[cam_id].points2d, dtype=np.float64)).cuda()
+            private_cache[cam_id] = ops.smooth_pose2d(pts).cpu().numpy()
+        return private_cache[cam_id]
 
     def save(self):
         """Writes the result pickle (core.py:349-369)."""
@@ -204,7 +224,7 @@ class Core:
             self.camNet.triangulate()
             pts3d = self.camNet.points3d
             out["points3d_wo_procrustes"] = pts3d
-            out["points3d"] = procrustes_seperate(pts3d)
+            out["points3d"] = self._procrustes_device(pts3d)
             out = {**self.camNet.summarize(), **out}
             self.points3d = out["points3d"]
         else:
@@ -216,6 +236,14 @@ class Core:
         print(f"Saved results at: {self.save_path}")
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _procrustes_device(pts3d):
+        import torch
+
+        from . import ops
+
+        return ops.procrustes(torch.as_tensor(np.ascontiguousarray(pts3d, dtype=np.float64)).cuda()).cpu().numpy()
+
     def setup_camera_ordering(self, camera_ordering):
         if camera_ordering is None:
             camera_ordering = find_default_camera_ordering(self.input_folder)

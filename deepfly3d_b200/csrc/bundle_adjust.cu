@@ -160,6 +160,65 @@ __device__ __forceinline__ bool inv3_spd(const double (&A)[3][3], double (&Ai)[3
   return true;
 }
 
+// M = D (D V D + reg I)^-1 D for a point seen by ONE camera.  V = Jp^T Jp has rank 2 and the explicit 3x3 inverse
+// carries a 1 / reg eigenvalue along the viewing ray; every use of M applies it to a vector of the row space of
+// Jp (W^T x = Jp^T Jc x, g_p = Jp^T r), where that eigenvalue multiplies an exact zero -- in floating point a
+// rounding residue, amplified by 1 / reg ~ 1e12 into the reduced camera system.  The restriction of M to the row
+// space has a closed form without the blow-up (push-through identity):
+//   M = D Jh^T (G + reg I)^-1 G^-1 Jh D,   Jh = Jp D,  G = Jh Jh^T (2 x 2, well conditioned).
+// SciPy's LSMR step is the minimum-norm one and never moves along the ray either.
+__device__ __forceinline__ bool single_view_M(const double (&Jp)[2][3], const double (&d)[3], double reg, double (&Mm)[3][3]) {
+  double Jh[2][3];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Jh[a][k] = Jp[a][k] * d[k];
+  const double g00 = Jh[0][0] * Jh[0][0] + Jh[0][1] * Jh[0][1] + Jh[0][2] * Jh[0][2];
+  const double g01 = Jh[0][0] * Jh[1][0] + Jh[0][1] * Jh[1][1] + Jh[0][2] * Jh[1][2];
+  const double g11 = Jh[1][0] * Jh[1][0] + Jh[1][1] * Jh[1][1] + Jh[1][2] * Jh[1][2];
+  const double det = g00 * g11 - g01 * g01;
+  const double r00 = g00 + reg, r11 = g11 + reg;
+  const double detr = r00 * r11 - g01 * g01;
+  if (!(det > 0.0) || !(detr > 0.0)) return false;
+  // H = (G + reg I)^-1 G^-1 (the two inverses commute: H is symmetric)
+  const double a00 = r11 / detr, a01 = -g01 / detr, a11 = r00 / detr;
+  const double b00 = g11 / det, b01 = -g01 / det, b11 = g00 / det;
+  const double h00 = a00 * b00 + a01 * b01;
+  const double h01 = 0.5 * ((a00 * b01 + a01 * b11) + (a01 * b00 + a11 * b01));
+  const double h11 = a01 * b01 + a11 * b11;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Mm[i][j] = d[i] * d[j] * (Jh[0][i] * (h00 * Jh[0][j] + h01 * Jh[1][j]) + Jh[1][i] * (h01 * Jh[0][j] + h11 * Jh[1][j]));
+  return true;
+}
+
+// M = D (D V D + reg I)^-1 D of one point (zero when the point has no observation or the block is singular)
+__device__ __forceinline__ void point_M(unsigned mask, const double (&V)[3][3], const double (&JpLast)[2][3], const double (&d)[3],
+                                        double reg, double (&Mm)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Mm[i][j] = 0.0;
+  if (!mask) return;
+  if (__popc(mask) == 1) {
+    single_view_M(JpLast, d, reg, Mm);
+    return;
+  }
+  double Vh[3][3], Vi[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? reg : 0.0);
+  if (inv3_spd(Vh, Vi)) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Mm[i][j] = d[i] * Vi[i][j] * d[j];
+  }
+}
+
 // Last-block-done reduction of per-block partial vectors: entries [0, n_sum) are summed, [n_sum, n) take the
 // maximum, both in a fixed block order.  Returns true in every thread of the last block, after `out` is
 // complete and visible to it.
@@ -497,6 +556,7 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
     double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     double gp[3] = {0, 0, 0};
     double W[DF3D_MAX_CAMS][6][3];
+    double JpLast[2][3] = {{0, 0, 0}, {0, 0, 0}};  // Jacobian of the last visible camera (the only one of a 1-view point)
     unsigned mask = 0;
 
     // pass 1: per-camera blocks, V, gp, W
@@ -519,6 +579,10 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
       if (vis) {
         project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
         mask |= 1u << c;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) JpLast[a][i] = Jp[a][i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           gp[i] += Jp[0][i] * r[0] + Jp[1][i] * r[1];
@@ -549,17 +613,7 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
       double d[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) d[i] = 1.0 / ws.sinv_p[(size_t)g * 3 + i];
-      double Vh[3][3], Vi[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? reg : 0.0);
-      if (inv3_spd(Vh, Vi)) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) Mm[i][j] = d[i] * Vi[i][j] * d[j];
-      }
+      point_M(mask, V, JpLast, d, reg, Mm);
     }
 
     // pass 2: reduced system, upper block triangle (a <= b)
@@ -708,6 +762,7 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
     const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
     double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     double rp[3] = {0, 0, 0};  // sum Jp^T (r - Jc dcn)
+    double JpLast[2][3] = {{0, 0, 0}, {0, 0, 0}};
     unsigned mask = 0;
     for (int c = 0; c < C; ++c) {
       const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
@@ -715,6 +770,10 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
       mask |= 1u << c;
       double r[2], Jc[2][6], Jp[2][3];
       project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) JpLast[a][i] = Jp[a][i];
       double q[2];
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
@@ -737,16 +796,11 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
       d[i] = 1.0 / ws.sinv_p[(size_t)g * 3 + i];
       gh[i] = ws.gp[(size_t)g * 3 + i] * d[i];
     }
-    if (mask) {
-      double Vh[3][3], Vi[3][3];
+    if (mask) {  // pp = (D V D + reg I)^-1 D rp = D^-1 M rp
+      double Mm[3][3];
+      point_M(mask, V, JpLast, d, reg, Mm);
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Vh[i][j] = d[i] * V[i][j] * d[j] + (i == j ? reg : 0.0);
-      if (inv3_spd(Vh, Vi)) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) pp[i] = Vi[i][0] * d[0] * rp[0] + Vi[i][1] * d[1] * rp[1] + Vi[i][2] * d[2] * rp[2];
-      }
+      for (int i = 0; i < 3; ++i) pp[i] = (Mm[i][0] * rp[0] + Mm[i][1] * rp[1] + Mm[i][2] * rp[2]) / d[i];
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {

@@ -225,6 +225,7 @@ struct df3d_hg {
   bool timing = false;
   std::vector<cudaEvent_t> events;
   std::vector<int> timed_bc;  // images of each timed chunk of the last forward
+  int timed_stem_variant = 0;  // stem variant (1 three-plane, 2 gray) the last timed forward ran
 };
 
 namespace df3d {
@@ -1226,6 +1227,7 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
       hg->events.push_back(ev);
     }
     hg->timed_bc.clear();
+    hg->timed_stem_variant = gray ? 2 : 1;
   }
   for (size_t pi = 0; pi < pieces.size(); ++pi) {
     const Piece& pc = pieces[pi];
@@ -1334,6 +1336,7 @@ extern "C" int df3d_hg_read_timing(df3d_hg* hg, double* out8) {
       DF3D_CUDA(cudaEventSynchronize(hg->events[(ci * n_ops + oi) * 2 + 1]));
       DF3D_CUDA(cudaEventElapsedTime(&ms, hg->events[(ci * n_ops + oi) * 2], hg->events[(ci * n_ops + oi) * 2 + 1]));
       const Op& op = hg->ops[oi];
+      if (op.variant > 0 && op.variant != hg->timed_stem_variant) continue;  // the stem variant that did not run
       if (op.kind == OP_CONV || op.kind == OP_CHAIN) {
         conv_ms += ms;
         conv_flops += op.flops_per_image * hg->timed_bc[ci];

@@ -204,6 +204,79 @@ def reprojection_error(cam_rt, intr4, pts_xy, pts3d):
     return out[0] / out[1]
 
 
+_TEMPLATE_MEDIANS = {}
+
+
+def template_medians(device, template=None):
+    """(2, 30) float64 on the device: per half the 12 median bone lengths and the 6 x 3 median alignment-joint
+    coordinates of the procrustes template (constants of the template, df3d/procrustes.py:38-48, 102-116)."""
+    from .procrustes import bone_lengths, read_template_pose3d
+    from .skeleton import ALIGN_IDX
+
+    key = (str(device), None if template is None else id(template))
+    if key not in _TEMPLATE_MEDIANS or template is not None:
+        tmpl = read_template_pose3d() if template is None else np.asarray(template, dtype=np.float64)
+        half = tmpl.shape[1] // 2
+        rows = []
+        for h in range(2):
+            t = tmpl[:, h * half:(h + 1) * half]
+            rows.append(np.concatenate([np.median(bone_lengths(t), axis=0), np.median(t[:, ALIGN_IDX], axis=0).ravel()]))
+        val = torch.as_tensor(np.stack(rows), device=device)
+        if template is not None:
+            return val
+        _TEMPLATE_MEDIANS[key] = val
+    return _TEMPLATE_MEDIANS[key]
+
+
+def procrustes_workspace(T, device):
+    return torch.empty(lib.df3d_procrustes_workspace_bytes(int(T)) + 256, dtype=torch.uint8, device=device)
+
+
+def procrustes(pts3d, template=None, workspace=None):
+    """(T,38,3) float64 CUDA -> registered (T,38,3): df3d.procrustes.procrustes_seperate on the device (global
+    medians by radix select).  Enqueued on the current stream, no host synchronisation."""
+    _need_cuda(pts3d)
+    if pts3d.dtype != torch.float64 or pts3d.dim() != 3 or pts3d.shape[2] != 3:
+        raise ValueError("procrustes: expected a (T, J, 3) float64 tensor")
+    pts3d = pts3d.contiguous()
+    T, J, _ = pts3d.shape
+    out = torch.empty_like(pts3d)
+    if T == 0:
+        return out
+    ws = workspace if workspace is not None else procrustes_workspace(T, pts3d.device)
+    wp, wn = _aligned_ptr(ws)
+    check(lib.df3d_procrustes(_ptr(pts3d), T, J, _ptr(template_medians(pts3d.device, template)), _ptr(out), wp, wn, _stream()))
+    return out
+
+
+def one_euro_filter(pts, freq=100.0, mincutoff=0.1, beta=2.0, dcutoff=1.0, t_first=1):
+    """(T, J, D) float64 CUDA -> One-Euro filtered tracks (df3d.signal_util.filter_batch defaults; the 2-D variant
+    filter_batch_2d is mincutoff=0.0001, beta=30, t_first=0)."""
+    _need_cuda(pts)
+    if pts.dtype != torch.float64:
+        raise ValueError("one_euro_filter: float64 tensor required")
+    pts = pts.contiguous()
+    T = pts.shape[0]
+    n = int(pts.numel() // T) if T else 0
+    out = torch.empty_like(pts)
+    check(lib.df3d_one_euro_filter(_ptr(pts), T, n, float(freq), float(mincutoff), float(beta), float(dcutoff), int(t_first),
+                                   _ptr(out), _stream()))
+    return out
+
+
+def smooth_pose2d(points2d, window_size=20, std_thr=5.0):
+    """(T, J, 2) float64 CUDA pixel tracks -> df3d.signal_util.smooth_pose2d (pad = window edge replication)."""
+    _need_cuda(points2d)
+    if points2d.dtype != torch.float64:
+        raise ValueError("smooth_pose2d: float64 tensor required")
+    points2d = points2d.contiguous()
+    T = points2d.shape[0]
+    n = int(points2d.numel() // T) if T else 0
+    out = torch.empty_like(points2d)
+    check(lib.df3d_smooth_pose2d(_ptr(points2d), T, n, int(window_size), float(std_thr), _ptr(out), _stream()))
+    return out
+
+
 def intr_to_vec4(intr):
     """(C,3,3) camera matrices -> (C,4) fx, fy, cx, cy."""
     intr = np.asarray(intr, dtype=np.float64)

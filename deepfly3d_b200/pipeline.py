@@ -69,23 +69,33 @@ class Pose3DPipeline:
         p2d, pxy = ops.pack_points2d(idx, NUM_CAMERAS, T, self.engine.heatmap_shape, self.order, self.image_shape)
         return idx, conf, p2d, pxy
 
-    def ba_frame_subset(self, T_total):
-        """Indices of the frames the bundle adjustment uses: all of them (what the reference does), or a strided
-        subset of at most `ba_max_frames` (100 000 frames, BA on <= 1 000)."""
-        if self.ba_max_frames is None or T_total <= self.ba_max_frames:
-            return None
-        stride = -(-T_total // self.ba_max_frames)
-        return torch.arange(0, T_total, stride, device=self.device)
+    def ba_points(self, pxy, group=None):
+        """The 2-D points the bundle adjustment runs on, identical on every rank: all frames of all ranks (what the
+        reference does), or -- `ba_max_frames` set and exceeded -- every stride-th frame of the whole recording
+        (100 000 frames, BA on <= 1 000).  Ranks select their own frames first, so only
+        the subset crosses NVLink; a rank with one frame fewer pads with an unobserved frame (all zeros)."""
+        import torch.distributed as dist
+
+        T = pxy.shape[1]
+        world = dist.get_world_size(group) if group is not None else 1
+        rank = dist.get_rank(group) if group is not None else 0
+        total = T * world
+        if self.ba_max_frames is not None and total > self.ba_max_frames:
+            stride = -(-total // self.ba_max_frames)
+            sel = torch.arange((-rank * T) % stride, T, stride, device=pxy.device)
+            n_max = -(-T // stride)
+            local = torch.zeros((pxy.shape[0], n_max) + tuple(pxy.shape[2:]), dtype=pxy.dtype, device=pxy.device)
+            local[:, :sel.numel()] = pxy.index_select(1, sel)
+        else:
+            local = pxy
+        return gather_frames(local, group, dim=1) if group is not None else local.contiguous()
 
     def pose3d(self, pxy, group=None):
         """pts_xy (7,T,J,2) of this rank's frames -> cameras after BA (7,6), R (7,3,3), points3d (T,J,3)
         re-triangulated with the new cameras (core.py:355), BA report."""
         Cn, T, J, _ = pxy.shape
         cam = self.cam_rt0.clone()
-        ba_xy = gather_frames(pxy, group, dim=1) if group is not None else pxy   # every rank: all frames' 2-D points
-        sel = self.ba_frame_subset(ba_xy.shape[1])
-        if sel is not None:
-            ba_xy = ba_xy.index_select(1, sel).contiguous()
+        ba_xy = self.ba_points(pxy, group)
         P0, _ = ops.projection_matrices(cam, self.intr4)
         X = ops.triangulate_dlt(P0, ba_xy)
         key = (Cn, ba_xy.shape[1], J)

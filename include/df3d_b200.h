@@ -169,6 +169,38 @@ int df3d_reprojection_error(const double* cam_rt_dev, const double* intr_dev,
                             double* out_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Procrustes registration of the triangulated skeleton to the template pose, on the device.  Replaces
+ * df3d.procrustes.procrustes_seperate (df3d/procrustes.py:51-263, df3d/plot_util.py:85-91), run by Core.save
+ * (df3d/core.py:358) and Core.get_points3d (core.py:339).  Joints 0-18 and 19-37 are registered separately:
+ * scale = median over 12 bones of (template median length / median length), subtract the median of all points,
+ * orthogonal fit (reflection allowed, no scaling) of the median BODY_COXA / COXA_FEMUR joints.  The medians over
+ * all frames are radix selects on the device (numpy's even-count rule).
+ *
+ *   pts3d_dev            : (T,38,3) float64          out_dev : (T,38,3) float64 (may alias pts3d_dev: no)
+ *   template_medians_dev : 2 x 30 float64, per half: 12 median bone lengths of the template, then the median
+ *                          coordinates (6 joints x 3) of its alignment joints (a constant of the template)
+ * ------------------------------------------------------------------------------------------ */
+size_t df3d_procrustes_workspace_bytes(int T);
+int df3d_procrustes(const double* pts3d_dev, int T, int J, const double* template_medians_dev, double* out_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Temporal filters of the pose tracks.  Replace df3d.signal_util.filter_batch / filter_batch_2d (One-Euro filter,
+ * df3d/signal_util.py:31-132; used by Core.get_points3d, df3d/core.py:342) and smooth_pose2d
+ * (signal_util.py:135-160; Core.smooth_points2d, core.py:286-296).
+ *
+ *   pts_dev / out_dev : (T, n_tracks) float64, frame-major (n_tracks = joints x coordinates)
+ *   t_first           : 1 = time stamps (i+1)*0.1 (filter_batch), 0 = i*0.1 (filter_batch_2d).  As in the
+ *                       reference, the sampling frequency is re-derived from consecutive time stamps.
+ * The One-Euro recurrence is evaluated with the reference's operation order and no fused multiply-add:
+ * bit-identical to the Python implementation.
+ * ------------------------------------------------------------------------------------------ */
+int df3d_one_euro_filter(const double* pts_dev, int T, int n_tracks, double freq, double mincutoff, double beta,
+                         double dcutoff, int t_first, double* out_dev, void* stream);
+int df3d_smooth_pose2d(const double* pts_dev, int T, int n_tracks, int window_size, double std_thr, double* out_dev,
+                       void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Stacked-hourglass forward + decode.  Replaces the network forward inside
  * df2d.inference.inference_folder (call site df3d/core.py:177-185; hyper-parameters hinted at
  * df3d/config.py:18,33-36).  Convolutions run as tcgen05 implicit-GEMM tiles fed by TMA.

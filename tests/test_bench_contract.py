@@ -49,8 +49,12 @@ def test_committed_reference_line():
 
 
 def test_reference_arm_runs_on_cpu():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-frames", "1", "--frames", "64"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    st = d["cpu_baseline"]["stages"]                                  # per-stage seconds
+    assert {"hourglass_s", "argmax_s", "pack_s", "ba_s", "dlt_s", "procrustes_s"} <= set(st) and st["frames_3d"] == 64
+    assert abs(d["ms_per_step"] - 1000.0 * 64 / d["value"]) < 1e-6    # per STEP of the workload, not per frame
