@@ -259,6 +259,8 @@ def one_euro_filter(pts, freq=100.0, mincutoff=0.1, beta=2.0, dcutoff=1.0, t_fir
     T = pts.shape[0]
     n = int(pts.numel() // T) if T else 0
     out = torch.empty_like(pts)
+    if pts.numel() == 0:
+        return out
     check(lib.df3d_one_euro_filter(_ptr(pts), T, n, float(freq), float(mincutoff), float(beta), float(dcutoff), int(t_first),
                                    _ptr(out), _stream()))
     return out
@@ -273,6 +275,8 @@ def smooth_pose2d(points2d, window_size=20, std_thr=5.0):
     T = points2d.shape[0]
     n = int(points2d.numel() // T) if T else 0
     out = torch.empty_like(points2d)
+    if points2d.numel() == 0:
+        return out
     check(lib.df3d_smooth_pose2d(_ptr(points2d), T, n, int(window_size), float(std_thr), _ptr(out), _stream()))
     return out
 

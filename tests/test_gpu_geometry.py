@@ -238,6 +238,7 @@ def test_bundle_adjust_ragged_and_single_view_points(ops, golden):
     assert (n_views == 0).any() and (n_views == 1).any() and (n_views >= 4).any()
     cam, R1, X1, rep, err, _ = _run_ba(ops, c, pts)
     Ro, to, Xo, sol = _oracle_ba(c, pts)
+    print(f"ragged: {rep} vs scipy cost {sol.cost:.6f} nfev {sol.nfev} status {sol.status}; max |dX| {np.abs(X1 - Xo).max():.3e}")
     assert rep["n_obs"] == int(g.visibility(pts).sum())
     assert abs(rep["cost"] - sol.cost) < 1e-5 * sol.cost
     assert np.abs(X1 - Xo).max() < 1e-3
