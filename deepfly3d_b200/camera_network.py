@@ -83,6 +83,13 @@ class CameraNetwork:
             else:
                 self.cam_list.append(Camera(c, self.points2d[c], k["R"], k["tvec"], k["intr"], k["distort"]))
         self._calibrated = calib is not None
+        # the kernels implement the reference's call -- pin-hole, update_distort=False on an all-zero distortion
+        # (data/calib.pkl) and no skew; a calibration that carries either would be silently mis-projected
+        for cam in self.cam_list:
+            if np.any(cam.distort != 0) or cam.intr[0, 1] != 0:
+                raise NotImplementedError(
+                    f"camera {cam.cam_id}: non-zero lens distortion / skew is not supported by the CUDA projection "
+                    "(the reference's packaged calibration has none, df3d/core.py:234-250)")
         self.points3d = None
         # (x, y) = (col, row) pixel coordinates on the device, the layout the kernels take
         self._pts_xy = torch.as_tensor(self.points2d[..., ::-1].copy(), device=self.device)

@@ -68,10 +68,12 @@ enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, k
 // per stage when done in sequence.
 struct StageLite {
   unsigned long long out;  // bf16 output base or 0
-  int n, kblocks, has_res, x_src, kind, col0, col1, aff_off, unit, hz, hzd, pad;
+  unsigned long long pool_raw, pool_act;  // pooled outputs or 0
+  int n, kblocks, has_res, x_src, kind, col0, col1, aff_off, unit, hz, hzd, pool_off;
 };
-static_assert(sizeof(StageLite) == 56, "StageLite layout");
-constexpr int kLiteStride = 64;
+static_assert(sizeof(StageLite) == 72, "StageLite layout");
+constexpr int kLiteStride = 80;
+static_assert(8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 32 + 8 * 4 * kMaxChain + kMaxChain * kLiteStride <= kChainBarBytes, "barrier area");
 
 // kProbe: the time-stamp probe of tools/chain_probe.cu (launch_conv_chain picks that instantiation when
 // ChainParams::dbg is set); the production instantiation carries none of its branches.
@@ -167,6 +169,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     l->unit = st.unit_scale;
     l->hz = st.hz_stage;
     l->hzd = st.hz_delta;
+    l->pool_raw = reinterpret_cast<unsigned long long>(st.pool_raw);
+    l->pool_act = reinterpret_cast<unsigned long long>(st.pool_act);
+    l->pool_off = st.pool_off;
   }
   // per-channel epilogue constants of every stage -> shared memory, only the arrays the stage uses:
   // [scale1 n (unless it is 1)][shift1 n][scale2 n][shift2 n (when the operand is relu(bn2(.)))]
@@ -182,6 +187,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       for (int c = threadIdx.x; c < st.n; c += kChainThreads) {
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (st.n + c)), "f"(st.scale2[c]));
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 4u * (2 * st.n + c)), "f"(st.shift2[c]));
+      }
+    }
+    if (st.pool_raw) {
+      const uint32_t p0 = aff_base + 4u * (uint32_t)st.pool_off;
+      for (int c = threadIdx.x; c < st.n; c += kChainThreads) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(p0 + 4u * c), "f"(st.pool_scale[c]));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(p0 + 4u * (st.n + c)), "f"(st.pool_shift[c]));
       }
     }
   }
@@ -607,11 +619,66 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           if (x_src) epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluX
           else       epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiReluOut
         }
+        if (x_src) {  // this slab = one K block of the next stage's operand: hand it to the MMA warp first (the stores
+                      // and the pooling below are off the chain's critical path)
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(epislab_l(i, sl));
+        }
         if (has_res && st.out) {
           // in-place output: this warp's 32 rows of the slab go out as one TMA store; the slab is handed back
           // to the producer once the store has read it -- one slab later, so that nobody waits for that
           fence_proxy_async();
           __syncwarp();
+          if (st.pool_raw) {
+            // 2x2 max-pool of the warp's own quarter (4 rows of the 8-wide tile = 2 x 4 pooling windows) straight
+            // from the slab: 8 pooled pixels x 8 sixteen-byte chunks, two items per lane, stored directly (the 8
+            // chunks of a pooled pixel are 128 contiguous bytes)
+            const uint32_t R0 = 4u * (uint32_t)q;            // first tile row of the quarter
+            const int rows_img = p.th;                         // tile rows per image
+            const int qn = n0 + (int)R0 / rows_img, qy = y0 + (int)R0 % rows_img;
+            const float* const pc = reinterpret_cast<const float*>(sm + (aff_base - smem_base)) + st.pool_off;
+#pragma unroll
+            for (int it2 = 0; it2 < 2; ++it2) {
+              const uint32_t item = (uint32_t)lane + 32u * it2;
+              const uint32_t ppx = item >> 3, chunk = item & 7u;
+              const uint32_t m0 = 32u * (uint32_t)q + (ppx >> 2) * 16u + 2u * (ppx & 3u);
+              auto ldc = [&](uint32_t mm) { return lds128(slab + mm * 128u + ((chunk ^ (mm & 7u)) << 4)); };
+              const uint4 a = ldc(m0), b = ldc(m0 + 1u), c = ldc(m0 + 8u), d = ldc(m0 + 9u);
+              auto mx2 = [](uint32_t x, uint32_t y) {
+                uint32_t r;
+                asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+                return r;
+              };
+              uint4 mx;
+              mx.x = mx2(mx2(a.x, b.x), mx2(c.x, d.x));
+              mx.y = mx2(mx2(a.y, b.y), mx2(c.y, d.y));
+              mx.z = mx2(mx2(a.z, b.z), mx2(c.z, d.z));
+              mx.w = mx2(mx2(a.w, b.w), mx2(c.w, d.w));
+              const int cc = sl * 64 + (int)chunk * 8;
+              const float4 sa = *reinterpret_cast<const float4*>(pc + cc), sb = *reinterpret_cast<const float4*>(pc + cc + 4);
+              const float4 ha = *reinterpret_cast<const float4*>(pc + st.n + cc), hb = *reinterpret_cast<const float4*>(pc + st.n + cc + 4);
+              uint4 act;
+              {
+                float2 v;
+                v = ffma2(bf2_unpack(mx.x), make_float2(sa.x, sa.y), make_float2(ha.x, ha.y));
+                act.x = pack2_relu(v.x, v.y);
+                v = ffma2(bf2_unpack(mx.y), make_float2(sa.z, sa.w), make_float2(ha.z, ha.w));
+                act.y = pack2_relu(v.x, v.y);
+                v = ffma2(bf2_unpack(mx.z), make_float2(sb.x, sb.y), make_float2(hb.x, hb.y));
+                act.z = pack2_relu(v.x, v.y);
+                v = ffma2(bf2_unpack(mx.w), make_float2(sb.z, sb.w), make_float2(hb.z, hb.w));
+                act.w = pack2_relu(v.x, v.y);
+              }
+              if (qn < p.B && !(kProbe && (p.dbg_exec & 2))) {
+                const int py = (qy >> 1) + (int)(ppx >> 2), px = (x0 >> 1) + (int)(ppx & 3u);
+                const size_t off = ((((size_t)qn * (p.H >> 1) + py) * (p.W >> 1) + px) * (size_t)st.n + (size_t)cc) * 2;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.pool_raw) + off) = mx;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.pool_act) + off) = act;
+              }
+            }
+          }
           if (lane == 0) {
             if (!(kProbe && (p.dbg_exec & 2))) tma_store_4d(&p.st[i].tmOutQ, slab + (uint32_t)q * 4096u, sl * 64, x0 + qx, y0 + qy, n0 + qn);
             tma_store_commit();
@@ -624,12 +691,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         } else if (has_res) {  // slab consumed by this warp
           __syncwarp();
           if (lane == 0) mbar_arrive(sempty(su));
-        }
-        if (x_src) {  // this slab = one K block of the next stage's operand: hand it to the MMA warp now
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(epislab_l(i, sl));
         }
       }
       if (has_res) {
@@ -806,6 +867,13 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
     }
     st.aff_off = aff_floats;
     aff_floats += st.n * ((st.unit_scale ? 1 : 2) + (st.x_src == 2 ? 2 : 0));
+    if (st.pool_raw) {
+      DF3D_REQUIRE(st.has_res && st.out_raw && st.pool_act && st.pool_scale && st.pool_shift && p.tw == 8 && p.th % 4 == 0 &&
+                       p.H % 2 == 0 && p.W % 2 == 0,
+                   DF3D_EUNSUPPORTED, "launch_conv_chain: the pooled output needs a stored stage with a residual on 8-wide tiles");
+      st.pool_off = aff_floats;
+      aff_floats += 2 * st.n;
+    }
     any_slab |= st.has_res != 0;
     any_res2 |= st.has_res2 != 0;
   }

@@ -32,6 +32,14 @@ struct ChainStage {
   const float* shift2;
   __nv_bfloat16* out_raw;  // bf16 output of this stage, NHWC with `n` channels per pixel, or null (stored through tmOutQ
                            // from the residual slab when the stage has a residual, else by 256-bit stores)
+  // 2x2 max-pool of out_raw taken in the epilogue (stages with a residual and out_raw on 8-wide tiles): each epilogue
+  // warp pools its own 4 x 8 pixel quarter of the slab it has just written in place and stores
+  //   pool_raw = max,  pool_act = bf16(relu(max * pool_scale[c] + pool_shift[c]))      (NHWC at half resolution, n channels)
+  // -- what maxpool_bn_relu_kernel computes from the stored tensor, without the extra pass over HBM
+  __nv_bfloat16* pool_raw;
+  __nv_bfloat16* pool_act;
+  const float* pool_scale;
+  const float* pool_shift;
   int n;         // output channels: 128 or 256
   int kblocks;   // K / 64 (head: taps * Cin/64; later stages: n of the previous stage / 64)
   int relu1;
@@ -43,6 +51,7 @@ struct ChainStage {
   int hz_stage;  // epilogue that must have drained those columns before this stage is issued (-1: implied)
   int hz_delta;  // ... of this tile (0) or of the previous one (1)
   int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)
+  int pool_off;  // ... of the pooled output's scale / shift (filled by the launcher)
   int epi_kind;  // specialised epilogue variant (filled by the launcher)
 };
 

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle: 1024-byte aligned tiles
   const int n_stages = p.n_stages, n_res = p.n_res_slots;
-  const bool has_res = n_res > 0, has_raw = p.out_raw != nullptr, has_act = p.out_act != nullptr;
+  const bool pool2 = p.pool2 != 0;
+  const bool has_res = n_res > 0, has_raw = p.out_raw != nullptr, has_act = p.out_act != nullptr || pool2;
   const bool has_res2 = has_res && p.has_res2 != 0;
   const uint32_t res_slot_bytes = kSlabBytes + (has_res2 ? kHalfSlabBytes : 0);
   // carve-up: [A/B ring][residual ring][raw out x2][act out x2][affine][barriers]
@@ -86,8 +87,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     prefetch_tensormap(&p.tmB);
     if (has_res) prefetch_tensormap(&p.tmRes);
     if (has_res2) prefetch_tensormap(&p.tmRes2);
-    if (has_raw) prefetch_tensormap(&p.tmRaw);
-    if (has_act) prefetch_tensormap(&p.tmAct);
+    if (has_raw && !pool2) prefetch_tensormap(&p.tmRaw);
+    if (has_act && !pool2) prefetch_tensormap(&p.tmAct);
+    if (pool2) {
+      prefetch_tensormap(&p.tmPoolRaw);
+      prefetch_tensormap(&p.tmPoolAct);
+    }
+    if (p.kb_split > 0) prefetch_tensormap(&p.tmA2);
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int ncol = p.n_tiles_n * BN;
     for (int i = threadIdx.x; i < ncol; i += kConvThreads) {
       float s1 = p.scale1[i], h1 = p.shift1[i], s2 = 0.f, h2 = 0.f;
-      if (has_act) {
+      if (p.scale2) {
         s2 = p.scale2[i];
         h2 = p.shift2[i];
       }
@@ -152,7 +158,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-          tma_load_4d(a_addr(stage), &p.tmA, full_bar(stage), kc * 64, x0 + dx, y0 + dy, n0);
+          const bool second = p.kb_split > 0 && kb >= p.kb_split;  // K-concatenation: the second activation tensor
+          tma_load_4d(a_addr(stage), second ? &p.tmA2 : &p.tmA, full_bar(stage), (second ? kc - p.kb_split : kc) * 64, x0 + dx,
+                      y0 + dy, n0);
           tma_load_2d(b_addr(stage), &p.tmB, full_bar(stage), kb * 64, nt * BN);
           if (++stage == (uint32_t)n_stages) {
             stage = 0;
@@ -354,8 +362,53 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               if (has_act) epi_slab<false, false, false, true, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
               else         epi_slab<false, false, false, true, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
             } else {
-              if (has_act) epi_slab<false, false, false, false, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
-              else         epi_slab<false, false, false, false, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+              if (has_act && !pool2) epi_slab<false, false, false, false, 2, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+              else                   epi_slab<false, false, false, false, 0, true, true>(t_slab, c1, h1, c2, h2, row, 0u, hh);
+            }
+            if (pool2) {
+              // 2x2 max-pool of this warp's quarter of the staged raw tile (32 consecutive pixels = whole pooling windows:
+              // two rows of a 16-wide tile or four rows of an 8-wide one -> 8 pooled pixels x 8 sixteen-byte chunks, two
+              // items per lane), then the next BatchNorm + ReLU on the pooled value, like maxpool_bn_relu_kernel
+              __syncwarp();
+              const uint32_t raw_tile = raw_base + obuf * kSlabBytes, pool_tile = act_base + obuf * kSlabBytes;
+#pragma unroll
+              for (int it2 = 0; it2 < 2; ++it2) {
+                const uint32_t item = (uint32_t)lane + 32u * it2;
+                const uint32_t ppx = item >> 3, chunk = item & 7u;
+                uint32_t m0;
+                if (p.tw == 16) m0 = 32u * q + 2u * ppx;
+                else            m0 = 32u * q + (ppx >> 2) * 16u + 2u * (ppx & 3u);
+                const uint32_t dn = (uint32_t)p.tw;  // pixel below
+                auto ldc = [&](uint32_t mm) { return lds128(raw_tile + mm * 128u + ((chunk ^ (mm & 7u)) << 4)); };
+                const uint4 a = ldc(m0), b = ldc(m0 + 1u), c = ldc(m0 + dn), d = ldc(m0 + dn + 1u);
+                auto mx2 = [](uint32_t x, uint32_t y) {
+                  uint32_t r;
+                  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+                  return r;
+                };
+                uint4 mx;
+                mx.x = mx2(mx2(a.x, b.x), mx2(c.x, d.x));
+                mx.y = mx2(mx2(a.y, b.y), mx2(c.y, d.y));
+                mx.z = mx2(mx2(a.z, b.z), mx2(c.z, d.z));
+                mx.w = mx2(mx2(a.w, b.w), mx2(c.w, d.w));
+                const uint32_t r8 = 8u * q + ppx;  // row of the pooled tile (box tw/2 x th/2)
+                const uint32_t off = r8 * 128u + ((chunk ^ (r8 & 7u)) << 4);
+                sts128(pool_tile + off, mx);
+                const int cc = nt * BN + sl * 64 + (int)chunk * 8;
+                const uint4 sa = lds128(aff_base + 2048u + 4u * cc), sb = lds128(aff_base + 2048u + 4u * cc + 16u);
+                const uint4 ha = lds128(aff_base + 3072u + 4u * cc), hb = lds128(aff_base + 3072u + 4u * cc + 16u);
+                const uint32_t s2[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const uint32_t h2v[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                const uint32_t mw[4] = {mx.x, mx.y, mx.z, mx.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float lo = fmaf(bf_lo(mw[e]), __uint_as_float(s2[2 * e]), __uint_as_float(h2v[2 * e]));
+                  const float hi = fmaf(bf_hi(mw[e]), __uint_as_float(s2[2 * e + 1]), __uint_as_float(h2v[2 * e + 1]));
+                  ow[e] = pack2_relu(lo, hi);
+                }
+                sts128(pool_tile + 4096u + off, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+              }
             }
           } else
 #pragma unroll
@@ -439,8 +492,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           named_bar_sync(bar_b, kEpiThreads);
           if (leader) {
             const int c0 = nt * BN + sl * 64;
-            if (has_raw) tma_store_4d(&p.tmRaw, raw_base + obuf * kSlabBytes, c0, x0, y0, n0);
-            if (has_act) tma_store_4d(&p.tmAct, act_base + obuf * kSlabBytes, c0, x0, y0, n0);
+            if (pool2) {
+              tma_store_4d(&p.tmPoolRaw, act_base + obuf * kSlabBytes, c0, x0 >> 1, y0 >> 1, n0);
+              tma_store_4d(&p.tmPoolAct, act_base + obuf * kSlabBytes + 4096u, c0, x0 >> 1, y0 >> 1, n0);
+            } else {
+              if (has_raw) tma_store_4d(&p.tmRaw, raw_base + obuf * kSlabBytes, c0, x0, y0, n0);
+              if (has_act) tma_store_4d(&p.tmAct, act_base + obuf * kSlabBytes, c0, x0, y0, n0);
+            }
             tma_store_commit();
           }
         }
@@ -538,7 +596,12 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
                DF3D_EUNSUPPORTED, "launch_conv_gemm: the fused arg-max needs the fp32 path (BN = 32), one image per tile");
   // shared-memory budget -> ring depths
   const int stage_bytes = kABytes + BN * 128;
-  const int fixed = 1024 + kAffBytes + kBarBytes + (p.out_raw ? 2 * kSlabBytes : 0) + (p.out_act ? 2 * kSlabBytes : 0);
+  DF3D_REQUIRE(!p.pool2 || (p.out_raw && !p.out_act && !p.residual && !p.relu1 && !p.out_f32 && p.scale2 && p.nb == 1 &&
+                            (p.tw == 16 || p.tw == 8) && p.th % 2 == 0 && BN >= 64),
+               DF3D_EUNSUPPORTED, "launch_conv_gemm: the pooled epilogue needs a plain bf16 output, one image per tile, 16- or 8-wide tiles");
+  DF3D_REQUIRE(p.kb_split == 0 || (p.taps == 1 && p.kb_split < p.kc_per_tap), DF3D_EUNSUPPORTED,
+               "launch_conv_gemm: K-concatenation needs a 1x1 conv and a split inside its K blocks");
+  const int fixed = 1024 + kAffBytes + kBarBytes + (p.out_raw ? 2 * kSlabBytes : 0) + ((p.out_act || p.pool2) ? 2 * kSlabBytes : 0);
   DF3D_REQUIRE(!p.has_res2 || (p.residual && p.tw % 2 == 0 && p.th % 2 == 0), DF3D_EUNSUPPORTED,
                "launch_conv_gemm: the half-resolution residual needs a full-resolution residual and an even tile");
   const int res_slot = kSlabBytes + (p.has_res2 ? kHalfSlabBytes : 0);

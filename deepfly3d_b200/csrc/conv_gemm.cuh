@@ -20,6 +20,16 @@ struct ConvParams {
   CUtensorMap tmRes2; // optional second residual at HALF resolution (nearest x2 up-sampled in the
                       // epilogue): box (64, tw/2, th/2, nb) of the (C, W/2, H/2, N) tensor
   int has_res2;
+  // K-concatenation (1x1 convs only): K blocks [kb_split, K/64) are read from a SECOND activation tensor through tmA2
+  // (same spatial size), e.g. conv3(t2) + downsample(x) of a bottleneck with a projection shortcut as ONE GEMM with
+  // the weights [W3 | Wds] side by side.  0: unused.
+  CUtensorMap tmA2;
+  int kb_split;
+  // pool2 != 0: the tile is 2x2 max-pooled in the epilogue (from the staged raw tile in shared memory) and only
+  // the pooled tensors go to HBM: tmPoolRaw = max, tmPoolAct = bf16(relu(max * scale2 + shift2)), boxes
+  // (64, tw/2, th/2, nb) of the (C, W/2, H/2, N) tensors.  Needs out_raw (its tensor map is not used), nb == 1.
+  CUtensorMap tmPoolRaw, tmPoolAct;
+  int pool2;
   int n_stages;       // A/B ring depth (filled by launch_conv_gemm from the shared-memory budget)
   int n_res_slots;    // residual ring depth (0 without residual)
   int taps;         // 1 (1x1) or 9 (3x3)

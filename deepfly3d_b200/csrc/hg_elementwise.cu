@@ -116,7 +116,7 @@ stem_im2col_kernel(const void* __restrict__ img, int dtype, const uint8_t* __res
 // Gray fast path of the stem: the three input planes are the same image (x/255 - mean with one
 // common mean), so the 7x7x3 conv is a 7x7x1 conv with the weights summed over the input channel and
 // the patch matrix has 49 (padded to 64) columns instead of 147 (192).
-constexpr int kGrayMaxW = 1024;  // widest input row staged in shared memory
+constexpr int kGrayMaxW = kStemGrayMaxW;  // widest input row staged in shared memory
 
 // One CTA = one output row of one image.  The seven input rows feeding it are staged in shared memory as
 // bf16 bits through a 256-entry table of bf16(u8 / 255 - mean) (the same expression and rounding as the

@@ -8,6 +8,7 @@ namespace df3d {
 
 constexpr int kStemKPadCols = 192;  // 7*7*3 = 147 patch columns, zero padded to 3 x 64
 constexpr int kStemKGray = 64;      // gray fast path: 7*7 = 49 patch columns, zero padded to 64
+constexpr int kStemGrayMaxW = 1024; // widest input row the gray fast path stages in shared memory
 
 int launch_stem_im2col(const void* img, int dtype, const uint8_t* flip, int B, int H, int W, const float mean[3],
                        __nv_bfloat16* out, cudaStream_t s);

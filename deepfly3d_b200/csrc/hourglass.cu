@@ -312,6 +312,31 @@ struct Emitter {
     }
     return o;
   }
+  // K-concatenation of two 1x1 convs with the same outputs: [CoutPad][a.cin + b.cin], a's inputs first
+  size_t pack_weights_concat(const Convp& a, const Convp& b, int CoutPad) {
+    const size_t K = (size_t)a.cin + b.cin;
+    size_t o = w_cursor;
+    w_cursor += (size_t)CoutPad * K;
+    if (dry) {
+      hg->wblob.resize(w_cursor, 0);
+      for (int co = 0; co < a.cout; ++co) {
+        for (int ci = 0; ci < a.cin; ++ci) hg->wblob[o + (size_t)co * K + ci] = f2bf(a.w[(size_t)co * a.cin + ci]);
+        for (int ci = 0; ci < b.cin; ++ci) hg->wblob[o + (size_t)co * K + a.cin + ci] = f2bf(b.w[(size_t)co * b.cin + ci]);
+      }
+    }
+    return o;
+  }
+  // epilogue affine of that sum: scale 1, shift = both biases
+  Affine concat_affine(const Convp& a, const Convp& b, int pad) {
+    Affine af{areserve(pad), areserve(pad)};
+    if (dry)
+      for (int i = 0; i < pad; ++i) {
+        hg->ablob[af.scale_off + i] = i < a.cout ? 1.0f : 0.0f;
+        hg->ablob[af.shift_off + i] = i < a.cout ? a.bias[i] + b.bias[i] : 0.0f;
+      }
+    return af;
+  }
+
   // stem: K index = (ky*7+kx)*3 + c  (must match stem_im2col_kernel), padded to 192
   size_t pack_stem(const Convp& c) {
     const size_t K = kStemKPadCols;
@@ -358,7 +383,8 @@ struct Emitter {
   // K = taps*CinPad.  Outputs may be invalid tensors (skipped).
   void conv(const Tensor& in, size_t w_off, int taps, int CinPad, int CoutPad, int BN, Affine a1, bool relu1,
             const Tensor* residual, const Tensor* out_raw, const Affine* a2, const Tensor* out_act,
-            const Tensor* out_f32, double flop_per_px, const Tensor* res2_half = nullptr) {
+            const Tensor* out_f32, double flop_per_px, const Tensor* res2_half = nullptr, const Tensor* in2 = nullptr,
+            const Tensor* pool_raw = nullptr, const Tensor* pool_act = nullptr) {
     ++n_ops;
     if (err) return;
     if (dry) return;
@@ -375,6 +401,10 @@ struct Emitter {
     if ((err = make_tmap_wgt(&p.tmB, hg->d_w + w_off, taps * CinPad, CoutPad, BN))) return;
     p.taps = taps;
     p.kc_per_tap = CinPad / 64;
+    if (in2 && in2->valid) {  // K-concatenation: the last in2->C / 64 K blocks come from the second tensor
+      p.kb_split = (CinPad - in2->C) / 64;
+      if ((err = make_tmap_act(&p.tmA2, ptr(*in2), in2->C, in.W, in.H, B, tw, th, nb))) return;
+    }
     p.H = in.H;
     p.W = in.W;
     p.B = B;
@@ -412,6 +442,15 @@ struct Emitter {
     if (out_f32 && out_f32->valid) {
       p.out_f32 = reinterpret_cast<float*>(ptr(*out_f32));
       p.f32_ld = out_f32->C;
+    }
+    if (pool_raw && pool_raw->valid && pool_act && pool_act->valid && a2) {  // 2x2 max-pool in the epilogue
+      p.pool2 = 1;
+      p.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*pool_raw));  // marks "bf16 output"; the stores go through tmPool*
+      p.raw_ld = pool_raw->C;
+      p.scale2 = hg->d_a + a2->scale_off;
+      p.shift2 = hg->d_a + a2->shift_off;
+      if ((err = make_tmap_box(&p.tmPoolRaw, ptr(*pool_raw), pool_raw->C, in.W / 2, in.H / 2, B, tw / 2, th / 2, nb))) return;
+      if ((err = make_tmap_box(&p.tmPoolAct, ptr(*pool_act), pool_act->C, in.W / 2, in.H / 2, B, tw / 2, th / 2, nb))) return;
     }
     hg->ops.push_back(op);
   }
@@ -505,7 +544,18 @@ struct Emitter {
     int x_src = 0;     // 0: last stage, 1: next stage takes bf16(v), 2: relu(bn(bf16(v))) with a2
     Affine a2{};
     double flop_per_px = 0.0;
+    // 2x2 max-pool of out_raw in the epilogue: pooled raw / relu(bn(pooled)) tensors at half resolution
+    const Tensor* pool_raw = nullptr;
+    const Tensor* pool_act = nullptr;
+    Affine pool_aff{};
   };
+
+  // the chain kernel pools in its epilogue on 8-wide tiles (halo-mode 8 x 16 tiles, or maps 8 pixels wide)
+  bool chain_pools(int H, int W) const {
+    if (hg->fuse < 2 || getenv("DF3D_HG_NO_POOL_FUSE")) return false;
+    const bool halo = H >= 16 && W >= 8 && H % 16 == 0 && W % 8 == 0 && !getenv("DF3D_HG_NO_HALO");
+    return (halo || W == 8) && H % 2 == 0;
+  }
 
   // One chain launch: head conv (taps x CinPad from `in`) + point-wise stages on the same tiles.
   void chain(const Tensor& in, int taps, int CinPad, const StageSpec* sp, int n) {
@@ -579,6 +629,13 @@ struct Emitter {
         if (st.has_res && (err = make_tmap_quarter(&st.tmOutQ, ptr(*s.out_raw), s.N, in.W, in.H, B, tw, th, nb))) return;
         bytes_px += 2.0 * s.N;
       }
+      if (s.pool_raw && s.pool_raw->valid && s.pool_act && s.pool_act->valid) {
+        st.pool_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*s.pool_raw));
+        st.pool_act = reinterpret_cast<__nv_bfloat16*>(ptr(*s.pool_act));
+        st.pool_scale = hg->d_a + s.pool_aff.scale_off;
+        st.pool_shift = hg->d_a + s.pool_aff.shift_off;
+        bytes_px += 2.0 * s.N * 0.5;  // two tensors at a quarter of the pixels
+      }
       op.flops_per_image += s.flop_per_px * in.H * in.W;
     }
     op.chain_bytes_per_image = bytes_px * in.H * in.W;
@@ -598,8 +655,10 @@ struct Emitter {
   //   y = conv3(relu(bn3(conv2(t1)))) + res (+ nearest_x2(up_add));   t1n = relu(next.bn2(next.conv1(relu(next.bn1(y)))))
   // fuse == 2: one chain launch [3x3 -> conv3 -> next.conv1];  fuse == 1: 3x3 alone, then [conv3 -> next.conv1].
   // t1 is consumed (freed).  `res` must have 2*planes channels (the caller applies a projection shortcut).
+  // pool_bn != null: y is also needed 2x2 max-pooled (raw in *pool_p, relu(pool_bn(.)) in *pool_pa); the chain's
+  // epilogue produces them when it can (chain_pools), otherwise the stand-alone pool kernel runs behind it.
   void tail(const Bott& b, const Tensor& res, Tensor& t1, const Bott* next, Tensor* y, Tensor* t1n,
-            const Tensor* up_add = nullptr) {
+            const Tensor* up_add = nullptr, const BNp* pool_bn = nullptr, Tensor* pool_p = nullptr, Tensor* pool_pa = nullptr) {
     const int H = res.H, W = res.W, P = b.planes, O = 2 * b.planes;
     StageSpec sp[3];
     int n = 0;
@@ -650,6 +709,13 @@ struct Emitter {
       s.x_src = next ? 2 : 0;
       s.a2 = an;
       s.flop_per_px = fpp(b.c3);
+      if (pool_bn && chain_pools(H, W)) {
+        s.pool_aff = bn_affine(*pool_bn, O);
+        *pool_p = talloc(H / 2, W / 2, O);
+        *pool_pa = talloc(H / 2, W / 2, O);
+        s.pool_raw = pool_p;
+        s.pool_act = pool_pa;
+      }
     }
     if (next) {
       StageSpec& s = sp[n++];
@@ -668,20 +734,22 @@ struct Emitter {
       chain(t2, 1, P, sp, n);
       tfree(t2);
     }
+    if (pool_bn && !pool_p->valid) pool(*y, *pool_bn, pool_p, pool_pa);
   }
 
   // fused form of hourglass(): x raw, t1_up = conv1 of hg[n-1][0] already applied to x.
-  void hourglass_f(const StackP& s, int n, const Tensor& x, Tensor& t1_up, const Bott* next, Tensor* o, Tensor* t1_o) {
-    Tensor p, pa;
-    pool(x, s.hg[n - 1][1].bn1, &p, &pa);
+  // p / pa: x max-pooled (raw, and activated by hg[n-1][1].bn1), produced by whoever produced x; consumed here
+  void hourglass_f(const StackP& s, int n, const Tensor& x, Tensor& t1_up, const Bott* next, Tensor* o, Tensor* t1_o,
+                   Tensor& p, Tensor& pa) {
     Tensor t1 = conv1(s.hg[n - 1][1], pa);
     tfree(pa);
-    Tensor l1, t1n;
-    tail(s.hg[n - 1][1], p, t1, n > 1 ? &s.hg[n - 2][0] : &s.hg[0][3], &l1, &t1n);
+    Tensor l1, t1n, lp, lpa;
+    tail(s.hg[n - 1][1], p, t1, n > 1 ? &s.hg[n - 2][0] : &s.hg[0][3], &l1, &t1n, nullptr,
+         n > 1 ? &s.hg[n - 2][1].bn1 : nullptr, &lp, &lpa);
     tfree(p);
     Tensor l2, t1l3;
     if (n > 1)
-      hourglass_f(s, n - 1, l1, t1n, &s.hg[n - 1][2], &l2, &t1l3);
+      hourglass_f(s, n - 1, l1, t1n, &s.hg[n - 1][2], &l2, &t1l3, lp, lpa);
     else
       tail(s.hg[0][3], l1, t1n, &s.hg[0][2], &l2, &t1l3);
     tfree(l1);
@@ -693,7 +761,7 @@ struct Emitter {
   }
 
   // stacks of the fused plan; x0 = output of layer3 (raw), t1 = conv1 of stack 0's hg[3][0] applied to it
-  void stacks_fused(Tensor x0, Tensor t1) {
+  void stacks_fused(Tensor x0, Tensor t1, Tensor xp, Tensor xpa) {
     const df3d_hg_desc& d = hg->desc;
     const NetP& net = hg->net;
     const int H4 = d.in_h / 4, W4 = d.in_w / 4;
@@ -701,7 +769,7 @@ struct Emitter {
     for (int i = 0; i < S; ++i) {
       const StackP& s = net.stacks[i];
       Tensor h, t1r;
-      hourglass_f(s, kDepth, x0, t1, &s.res, &h, &t1r);
+      hourglass_f(s, kDepth, x0, t1, &s.res, &h, &t1r, xp, xpa);
       const bool last = i == S - 1;
       // [res.conv2 ->] res.conv3 + h -> fc + BN + ReLU [-> merged re-injection + x0 -> next stack's first conv1]
       const Bott& b = s.res;
@@ -767,6 +835,13 @@ struct Emitter {
           q.x_src = 2;
           q.a2 = bn_affine(nb0.bn1, kCh);
           q.flop_per_px = fpp(s.fc_) + fpp(s.score) + fpp(s.score_);
+          if (chain_pools(H4, W4)) {  // the next stack pools its input first: done here, in this stage's epilogue
+            q.pool_aff = bn_affine(net.stacks[i + 1].hg[kDepth - 1][1].bn1, kCh);
+            xp = talloc(H4 / 2, W4 / 2, kCh);
+            xpa = talloc(H4 / 2, W4 / 2, kCh);
+            q.pool_raw = &xp;
+            q.pool_act = &xpa;
+          }
         }
         {
           StageSpec& q = sp[n++];  // first conv1 of the next stack
@@ -813,6 +888,7 @@ struct Emitter {
       } else {
         x0 = nx;
         t1 = t1x;
+        if (!xp.valid) pool(x0, net.stacks[i + 1].hg[kDepth - 1][1].bn1, &xp, &xpa);
       }
     }
   }
@@ -906,13 +982,42 @@ struct Emitter {
     if (!dry && !err) hg->ops.back().variant = 2;
     tfree(col);
 
-    Tensor y1, none;
-    bottleneck(net.layer1, x, xa, nullptr, &y1, &none);
-    tfree(x);
-    tfree(xa);
+    Tensor none;
     Tensor p, pa;
-    pool(y1, net.layer2.bn1, &p, &pa);
-    tfree(y1);
+    if (getenv("DF3D_HG_NO_FRONT_FUSE")) {  // profiling knob: the unfused front section (three more launches)
+      Tensor y1;
+      bottleneck(net.layer1, x, xa, nullptr, &y1, &none);
+      tfree(x);
+      tfree(xa);
+      pool(y1, net.layer2.bn1, &p, &pa);
+      tfree(y1);
+    } else {
+      // layer1 (64 -> 128 channels at half resolution, projection shortcut) + the 2x2 max-pool behind it:
+      //   conv1, conv2 as usual; conv3(t2) + downsample(x) is ONE GEMM over K = [t2 | x] (weights side by side, both
+      //   biases in the shift), and its epilogue pools the tile and applies layer2's first BatchNorm + ReLU -- the
+      //   full-resolution 128-channel tensor, the shortcut tensor and the pool launch never exist in HBM
+      const Bott& b = net.layer1;
+      const int P = b.planes, O = 2 * b.planes;
+      size_t w1 = pack_weights(b.c1, P, b.inpl);
+      Affine a1 = conv_affine(b.c1, &b.bn2, P);
+      Tensor t1 = talloc(H2, W2, P);
+      conv(xa, w1, 1, b.inpl, P, bn_for(P), a1, true, nullptr, &t1, nullptr, nullptr, nullptr, fpp(b.c1));
+      tfree(xa);
+      size_t w2 = pack_weights(b.c2, P, P);
+      Affine a2 = conv_affine(b.c2, &b.bn3, P);
+      Tensor t2 = talloc(H2, W2, P);
+      conv(t1, w2, 9, P, P, bn_for(P), a2, true, nullptr, &t2, nullptr, nullptr, nullptr, fpp(b.c2));
+      tfree(t1);
+      size_t w3 = pack_weights_concat(b.c3, b.ds, O);
+      Affine a3 = concat_affine(b.c3, b.ds, O);
+      Affine an = bn_affine(net.layer2.bn1, O);
+      p = talloc(H4, W4, O);
+      pa = talloc(H4, W4, O);
+      conv(t2, w3, 1, P + b.inpl, O, bn_for(O), a3, false, nullptr, nullptr, &an, nullptr, nullptr, fpp(b.c3) + fpp(b.ds), nullptr, &x,
+           &p, &pa);
+      tfree(t2);
+      tfree(x);
+    }
     Tensor y2, y2a;
     bottleneck(net.layer2, p, pa, &net.layer3.bn1, &y2, &y2a);
     tfree(p);
@@ -927,10 +1032,10 @@ struct Emitter {
       Tensor dres = talloc(H4, W4, kCh);
       conv(y2, wd, 1, 2 * kInplanes, kCh, 256, ad, false, nullptr, &dres, nullptr, nullptr, nullptr, fpp(net.layer3.ds));
       tfree(y2);
-      Tensor xf, t1x;
-      tail(net.layer3, dres, t1, &net.stacks[0].hg[kDepth - 1][0], &xf, &t1x);
+      Tensor xf, t1x, xp, xpa;
+      tail(net.layer3, dres, t1, &net.stacks[0].hg[kDepth - 1][0], &xf, &t1x, nullptr, &net.stacks[0].hg[kDepth - 1][1].bn1, &xp, &xpa);
       tfree(dres);
-      stacks_fused(xf, t1x);
+      stacks_fused(xf, t1x, xp, xpa);
       return;
     }
     Tensor x0, x0a;
@@ -1218,7 +1323,13 @@ extern "C" int df3d_hg_forward_argmax(df3d_hg* hg, const void* images_dev, int d
 
   const size_t n_ops = hg->ops.size();
   // gray fast path of the stem: uint8 gray input replicated to three planes with one common mean
-  const bool gray = dtype == 0 && hg->mean[0] == hg->mean[1] && hg->mean[1] == hg->mean[2] && !getenv("DF3D_HG_NO_GRAY");
+  // (rows wider than the fast path's shared-memory window take the generic three-plane variant)
+  const bool gray = dtype == 0 && hg->mean[0] == hg->mean[1] && hg->mean[1] == hg->mean[2] && d.in_w <= kStemGrayMaxW &&
+                    !getenv("DF3D_HG_NO_GRAY");
+  // the fused arg-max accumulates with atomicMax into keys that the decode kernel zeroes again; a forward that
+  // failed half-way would leave them dirty, so they are cleared up front (B x 32 x 8 bytes)
+  if (hg->score_nb == 1 || hg->lane_ops.empty())
+    DF3D_CUDA(cudaMemsetAsync(hg->d_keys, 0, (size_t)B * kHeatPad * sizeof(unsigned long long), s));
   const std::vector<Piece> pieces = cut_batch(hg, B);
   if (hg->timing) {
     while (hg->events.size() < pieces.size() * n_ops * 2) {
@@ -1391,7 +1502,7 @@ extern "C" int df3d_hg_op_timing(df3d_hg* hg, int op_index, double* ms_out, doub
                       (p.out_raw ? p.raw_ld : 0) + (p.out_act ? p.act_ld : 0)) +
           px * 4.0 * (p.out_f32 ? p.f32_ld : 0);
     snprintf(desc, desc_len, "conv%dx%d %4dx%-4d cin=%3d BN=%3d%s%s%s", p.taps == 9 ? 3 : 1, p.taps == 9 ? 3 : 1, p.H, p.W,
-             p.kc_per_tap * 64, op.BN, p.residual ? (p.has_res2 ? " +res+up" : " +res") : "", p.out_act ? " +act" : "",
+             p.kc_per_tap * 64, op.BN, p.residual ? (p.has_res2 ? " +res+up" : " +res") : "", p.pool2 ? " +pool" : (p.out_act ? " +act" : ""),
              p.out_f32 ? " f32" : "");
   } else if (op.kind == OP_CHAIN) {
     const ChainParams& p = op.chain;

@@ -39,14 +39,18 @@ class Bottleneck(nn.Module):
         if inplanes != planes * 2:
             self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 2, 1, bias=True))
 
-    def forward(self, x, rnd=lambda t: t, wq=lambda c: c.weight):
+    def forward(self, x, rnd=lambda t: t, wq=lambda c: c.weight, round_shortcut=True):
+        """round_shortcut=False (emulation only): the CUDA path evaluates conv3(t2) + downsample(x) of layer1 as one
+        GEMM over the concatenated inputs, so the projection shortcut is never rounded to bf16 on its own."""
         a = rnd(F.relu(self.bn1(x)))
         t1 = rnd(F.relu(self.bn2(F.conv2d(a, wq(self.conv1), self.conv1.bias))))
         t2 = rnd(F.relu(self.bn3(F.conv2d(t1, wq(self.conv2), self.conv2.bias, padding=1))))
         res = x
         if self.downsample is not None:
             ds = self.downsample[0]
-            res = rnd(F.conv2d(x, wq(ds), ds.bias))
+            res = F.conv2d(x, wq(ds), ds.bias)
+            if round_shortcut:
+                res = rnd(res)
         return rnd(F.conv2d(t2, wq(self.conv3), self.conv3.bias) + res)
 
 
@@ -113,7 +117,7 @@ class HourglassNet(nn.Module):
             x = rnd(F.relu(self.bn1(F.conv2d(x[:, :1], w1, self.conv1.bias, stride=2, padding=3))))
         else:
             x = rnd(F.relu(self.bn1(F.conv2d(x, wq(self.conv1), self.conv1.bias, stride=2, padding=3))))
-        x = self.layer1[0](x, rnd, wq)
+        x = self.layer1[0](x, rnd, wq, round_shortcut=not emulate_bf16)
         x = F.max_pool2d(x, 2, stride=2)
         x = self.layer2[0](x, rnd, wq)
         x = self.layer3[0](x, rnd, wq)

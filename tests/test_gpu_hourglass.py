@@ -149,3 +149,29 @@ def test_fused_plans_are_bit_identical(hgmod, monkeypatch, shape):
         assert torch.equal(outs[0][2], outs[k][2]), f"score maps differ between DF3D_HG_FUSE=0 and {k}"
         assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][1], outs[k][1])
     assert outs[2][3] < outs[1][3] < outs[0][3]        # fewer launches the more is chained
+
+
+def test_front_section_fusion_matches_unfused(hgmod, monkeypatch):
+    """Default plan: layer1's conv3 + projection shortcut as one K-concatenated GEMM whose epilogue max-pools the tile
+    (csrc/conv_gemm.cu: kb_split, pool2).  DF3D_HG_NO_FRONT_FUSE=1 runs the same layers as separate launches with the
+    shortcut rounded to bf16 on its own: the two must agree to bf16 rounding noise, and the arg-max of their own
+    maps must decode bit-exactly."""
+    model = ohg.make_model(2, seed=11)
+    img = ohg.to_uint8(ohg.synthetic_images(5, 256, 512, seed=12)).cuda()
+    flip = torch.tensor([0, 1, 0, 1, 1], dtype=torch.uint8).cuda()
+    outs = []
+    for knob in (None, "1"):
+        if knob:
+            monkeypatch.setenv("DF3D_HG_NO_FRONT_FUSE", knob)
+        eng = hgmod.HourglassEngine(model.state_dict(), 256, 512, max_batch=5)
+        idx, conf, heat = eng.forward(img, flip=flip, return_heatmap=True)
+        torch.cuda.synchronize()
+        outs.append((idx.cpu().numpy(), heat[..., :19].cpu(), eng.launches(5)))
+        eng.close()
+    rng_ = float(outs[1][1].max() - outs[1][1].min())
+    err = float((outs[0][1] - outs[1][1]).abs().max()) / rng_
+    print(f"  front fusion vs separate launches: heat err {err:.4f} of range, launches {outs[0][2]} vs {outs[1][2]}")
+    assert err < 0.01
+    assert outs[0][2] == outs[1][2] - 2
+    own_idx, _ = oargmax.heatmap_argmax(outs[0][1].permute(0, 3, 1, 2).contiguous().numpy())
+    assert np.array_equal(outs[0][0], own_idx)
