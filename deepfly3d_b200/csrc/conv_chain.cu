@@ -59,7 +59,7 @@ constexpr int kHaloPitch = 10;               // halo row = 8 tile pixels + one o
 constexpr int kHaloBytes = 18 * kHaloPitch * 128;  // one 64-channel half of the halo of an 8 x 16 tile (45 KB)
 constexpr int kColP = 0, kColQ = 128, kColR = 384;
 constexpr int kChainSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
-constexpr int kChainBarBytes = 1024;  // barriers, TMEM slot, StageLite table
+constexpr int kChainBarBytes = 1280;  // barriers, TMEM slot, StageLite table
 // specialised epilogues (see epi_slab)
 enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, kEpiResUpOut, kEpiResX };
 
@@ -69,10 +69,10 @@ enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, k
 struct StageLite {
   unsigned long long out;  // bf16 output base or 0
   unsigned long long pool_raw, pool_act;  // pooled outputs or 0
-  int n, kblocks, has_res, x_src, kind, col0, col1, aff_off, unit, hz, hzd, pool_off;
+  int n, kblocks, has_res, x_src, kind, col[2][2], aff_off, unit, hz, hzd, pool_off, ssk, pad;
 };
-static_assert(sizeof(StageLite) == 72, "StageLite layout");
-constexpr int kLiteStride = 80;
+static_assert(sizeof(StageLite) == 88, "StageLite layout");
+constexpr int kLiteStride = 96;
 static_assert(8 * (2 * kMaxM + 2 * kMaxSlabs + 2 * kMaxChain) + 32 + 8 * 4 * kMaxChain + kMaxChain * kLiteStride <= kChainBarBytes, "barrier area");
 
 // kProbe: the time-stamp probe of tools/chain_probe.cu (launch_conv_chain picks that instantiation when
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       if (p.st[i].has_res) prefetch_tensormap(&p.st[i].tmRes);
       if (p.st[i].has_res2) prefetch_tensormap(&p.st[i].tmRes2);
       if (p.st[i].has_res && p.st[i].out_raw) prefetch_tensormap(&p.st[i].tmOutQ);
+      if (p.st[i].ss_kblocks) prefetch_tensormap(&p.st[i].tmA2);
     }
     for (int s = 0; s < p.n_m; ++s) {
       mbar_init(mfull(s), 1);
@@ -163,8 +164,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     l->has_res = st.has_res;
     l->x_src = st.x_src;
     l->kind = st.epi_kind;
-    l->col0 = st.col[0];
-    l->col1 = st.col[1];
+    l->col[0][0] = st.col[0][0];
+    l->col[0][1] = st.col[0][1];
+    l->col[1][0] = st.col[1][0];
+    l->col[1][1] = st.col[1][1];
+    l->ssk = st.ss_kblocks;
     l->aff_off = st.aff_off;
     l->unit = st.unit_scale;
     l->hz = st.hz_stage;
@@ -278,8 +282,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         }
       };
       // one slot = this CTA's 64 rows of both 128-row halves of one K block (256 outputs) or of two K blocks (128)
-      auto load_weights = [&](int i) {
+      auto load_weights = [&](int i, int tile) {
         const int kbn = lite(i).kblocks, nh = lite(i).n >> 7;
+        // K blocks read from shared memory first (issue order of the MMA warp): one slot with this CTA's A tile of the
+        // second activation tensor, one with its 64 rows of both 128-row weight halves
+        if (const int ssk = lite(i).ssk) {
+          int x0, y0, n0;
+          decode_tile(tile, x0, y0, n0);
+          for (int kb = 0; kb < ssk; ++kb) {
+            uint32_t dst = acquire(kUnitBytes);
+            tma_load_4d_pair(dst, &p.st[i].tmA2, mfull_l(u), kb * 64, x0, y0, n0);
+            advance();
+            dst = acquire(2 * kSubBytes);
+            tma_load_2d_pair(dst, &p.st[i].tmB, mfull_l(u), (kbn + kb) * 64, brow);
+            tma_load_2d_pair(dst + kSubBytes, &p.st[i].tmB, mfull_l(u), (kbn + kb) * 64, 128 + brow);
+            advance();
+          }
+        }
         const int slots = (kbn * nh) >> 1;
         for (int sl = 0; sl < slots; ++sl) {
           const uint32_t dst = acquire(2 * kSubBytes);
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           if (head_step) {
             if (has_next) load_head(2 * (pt + pstride) + (int)rank);
           } else if (t >= 0) {
-            load_weights(sidx < head_after ? sidx + 1 : sidx);
+            load_weights(sidx < head_after ? sidx + 1 : sidx, 2 * pt + (int)rank);
           }
         }
         if (!has_next) break;
@@ -342,7 +361,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint64_t desc_hi = umma_smem_desc_sw128(0);  // everything but the 14-bit start address
     const uint32_t n_m = (uint32_t)p.n_m;
     const int kb0 = p.st[0].kblocks;
-    const uint32_t d0 = tmem_base + (uint32_t)p.st[0].col[0], d1 = tmem_base + (uint32_t)p.st[0].col[1];
     const int hz0 = p.st[0].hz_stage, hz0_delta = p.st[0].hz_delta;
     uint32_t mu = 0, mph = 0;
     unsigned long long* const dbg = (kProbe && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
@@ -375,6 +393,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const uint64_t desc_halo = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32);  // group pitch
     uint32_t heads = 0;
     auto issue_head = [&](int t) {
+      const uint32_t d0 = tmem_base + (uint32_t)lite(0).col[t & 1][0], d1 = tmem_base + (uint32_t)lite(0).col[t & 1][1];
       if (kProbe && dbg && di < 4000) dbg[di++] = clock64();  // [head start]
       if (hz0 >= 0 && t - hz0_delta >= 0) mbar_wait_cluster(epidone(hz0), (uint32_t)(t - hz0_delta) & 1u);
       if (p.halo) {
@@ -442,10 +461,36 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const StageLite& L = lite(i);
       const StageLite& Lp = lite(i - 1);
       const int kbn = L.kblocks, nh = L.n >> 7;
-      const uint32_t c0 = tmem_base + (uint32_t)L.col0, c1 = tmem_base + (uint32_t)L.col1;
-      const uint32_t x0c = tmem_base + (uint32_t)Lp.col0, x1c = tmem_base + (uint32_t)Lp.col1;
+      const uint32_t c0 = tmem_base + (uint32_t)L.col[par][0], c1 = tmem_base + (uint32_t)L.col[par][1];
+      const uint32_t x0c = tmem_base + (uint32_t)Lp.col[par][0], x1c = tmem_base + (uint32_t)Lp.col[par][1];
       const int hz = L.hz, hzd = L.hzd;
       if (hz >= 0 && t - hzd >= 0) mbar_wait_cluster(epidone(hz), (uint32_t)(t - hzd) & 1u);  // accumulator columns drained
+      // K blocks whose A operand comes from shared memory (second activation tensor): independent of the previous
+      // epilogue, so they go first and keep the tensor pipe busy while that epilogue runs
+      const int ssk = L.ssk;
+      for (int kb = 0; kb < ssk; ++kb) {
+        ring_wait();
+        const uint32_t ua = mu;
+        const uint32_t a_addr = m_base + mu * slot_bytes;
+        const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+        ring_probe_next();
+        ring_advance();
+        ring_wait();
+        const uint32_t b_addr = m_base + mu * slot_bytes;
+        const uint64_t b0 = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+        const uint64_t b1 = desc_hi | (uint64_t)(((b_addr + kSubBytes) >> 4) & 0x3FFFu);
+        ring_probe_next();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(c0, adesc + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(c1, adesc + 2u * k, b1 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(mempty(ua));
+          umma_commit_pair(mempty(mu));
+        }
+        ring_advance();
+      }
+      const uint32_t acc0 = ssk ? 1u : 0u;  // the tensor-memory K blocks accumulate on top of those
       const int slots = (kbn * nh) >> 1;
 #pragma unroll 1
       for (int sl = 0; sl < slots; ++sl) {
@@ -468,9 +513,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           if (nh == 2) {  // K block sl, both output halves
             const uint32_t xa = ((sl >> 1) ? x1c : x0c) + (sl & 1) * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c0, xa + k * 8, b0 + 2u * k, idesc, (sl | k) != 0 ? 1u : acc0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c1, xa + k * 8, b1 + 2u * k, idesc, (sl | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(c1, xa + k * 8, b1 + 2u * k, idesc, (sl | k) != 0 ? 1u : acc0);
           } else {        // K blocks 2 sl and 2 sl + 1 of a 128-wide stage
             const uint32_t xa = sl ? x1c : x0c;  // K blocks 0,1 live in the first operand half, 2,3 in the second
 #pragma unroll
@@ -572,7 +617,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       __syncwarp();
       tc_fence_after();
       if (kProbe && dbg && di < dend) dbg[di++] = clock64();  // [stage i accumulator ready]
-      const uint32_t t_lo = tmem_base + lane_base + (uint32_t)st.col0, t_hi = tmem_base + lane_base + (uint32_t)st.col1;
+      const uint32_t t_lo = tmem_base + lane_base + (uint32_t)st.col[t & 1][0], t_hi = tmem_base + lane_base + (uint32_t)st.col[t & 1][1];
 #pragma unroll 1
       for (int sl = grp; sl < nsl; sl += 2) {
         uint32_t su = 0, slab = s_base;
@@ -772,8 +817,16 @@ int conv_chain_configure() {
 static int plan_tmem(ChainParams& p) {
   const int n = p.n_chain;
   auto set = [&](int i, int lo, int hi, int hz, int delta) {
-    p.st[i].col[0] = lo;
-    p.st[i].col[1] = hi;
+    p.st[i].col[0][0] = p.st[i].col[1][0] = lo;
+    p.st[i].col[0][1] = p.st[i].col[1][1] = hi;
+    p.st[i].hz_stage = hz;
+    p.st[i].hz_delta = delta;
+  };
+  auto set2 = [&](int i, int lo_e, int hi_e, int lo_o, int hi_o, int hz, int delta) {  // even / odd tiles differ
+    p.st[i].col[0][0] = lo_e;
+    p.st[i].col[0][1] = hi_e;
+    p.st[i].col[1][0] = lo_o;
+    p.st[i].col[1][1] = hi_o;
     p.st[i].hz_stage = hz;
     p.st[i].hz_delta = delta;
   };
@@ -802,6 +855,18 @@ static int plan_tmem(ChainParams& p) {
     set(3, kColQ, kColQ + 128, -1, 0);
     set(4, kColR, kColR, -1, 0);
     p.head_after = 3;
+  } else if (is({128, 256, 256, 128})) {
+    // inter-stack chain with res.conv3 and fc merged: four 128-column blocks P, Q0, Q1, R whose roles rotate with
+    // the tile parity so that the next head can go behind stage 2 (the heavy merged-skip epilogue):
+    //   even tile: head P | fc Q0+Q1 | skip R+P | conv1 Q0 | next head Q1
+    //   odd tile:  head Q1 | fc R+P  | skip Q0+Q1 | conv1 R | next head P
+    // hazards: fc overwrites the previous tile's skip accumulator (its epilogue 2), skip the previous conv1's (3)
+    const int Q0 = kColQ, Q1 = kColQ + 128;
+    set2(0, kColP, kColP, Q1, Q1, -1, 0);
+    set2(1, Q0, Q1, kColR, kColP, 2, 1);
+    set2(2, kColR, kColP, Q0, Q1, 3, 1);
+    set2(3, Q0, Q0, kColR, kColR, -1, 0);
+    p.head_after = 2;
   } else if (is({128, 256, 256})) {  // last stack: P | Q | P+R; the next head has to wait for the fc epilogue
     set(0, kColP, kColP, 2, 1);
     set(1, kColQ, kColQ + 128, -1, 0);
@@ -845,6 +910,8 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
     ChainStage& st = p.st[i];
     DF3D_REQUIRE(st.n == 128 || st.n == 256, DF3D_EUNSUPPORTED, "launch_conv_chain: stage %d has %d output channels (128 or 256)", i, st.n);
     DF3D_REQUIRE(i == 0 || st.kblocks * 64 == p.st[i - 1].n, DF3D_EINVAL, "launch_conv_chain: stage %d K does not match stage %d N", i, i - 1);
+    DF3D_REQUIRE(st.ss_kblocks == 0 || (i > 0 && st.n == 256 && st.ss_kblocks <= 4), DF3D_EUNSUPPORTED,
+                 "launch_conv_chain: shared-memory K blocks need a later stage with 256 outputs");
     DF3D_REQUIRE((i + 1 < p.n_chain) == (st.x_src != 0), DF3D_EINVAL, "launch_conv_chain: x_src must be set on every stage but the last");
     DF3D_REQUIRE(!st.has_res2 || (st.has_res && p.tw % 2 == 0 && p.th % 2 == 0), DF3D_EUNSUPPORTED,
                  "launch_conv_chain: the half-resolution residual needs a full-resolution residual and an even tile");

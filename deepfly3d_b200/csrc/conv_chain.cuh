@@ -42,12 +42,20 @@ struct ChainStage {
   const float* pool_shift;
   int n;         // output channels: 128 or 256
   int kblocks;   // K / 64 (head: taps * Cin/64; later stages: n of the previous stage / 64)
+  // Later stages may take `ss_kblocks` MORE K blocks whose A operand is a second activation tensor read from shared
+  // memory (tmA2, same tile as the head: box (64, tw, th, nb)) instead of the previous stage's result in tensor memory:
+  //   acc = W[:, :64 kblocks] * x_prev + W[:, 64 kblocks:] * a2
+  // -- e.g. fc(conv3(t) + h) = (W_fc W_3) t + W_fc h with t from the previous stage and h from HBM.  These MMAs do not
+  // depend on the previous epilogue and are issued first.  Needs n = 256.
+  CUtensorMap tmA2;
+  int ss_kblocks;
   int relu1;
   int unit_scale;  // scale1 is identically 1 (conv without a folded BatchNorm): the epilogue only adds shift1
   int has_res, has_res2;
   int x_src;     // operand handed to the next stage: 0 none (last stage), 1 raw, 2 act
   // tensor-memory plan (filled by launch_conv_chain, see plan_tmem)
-  int col[2];    // accumulator columns of channels [0,128) and [128,256) (the latter unused for n = 128)
+  int col[2][2]; // [tile parity][half]: accumulator columns of channels [0,128) and [128,256) (the latter unused for
+                 // n = 128); plans whose column assignment alternates between consecutive tiles differ by parity
   int hz_stage;  // epilogue that must have drained those columns before this stage is issued (-1: implied)
   int hz_delta;  // ... of this tile (0) or of the previous one (1)
   int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)

@@ -209,6 +209,7 @@ struct df3d_hg {
   std::vector<uint16_t> wblob;
   std::vector<float> ablob;
   std::vector<std::vector<float>> merged_w, merged_b;  // per-stack merged fc_/score_/score weights
+  std::vector<std::vector<float>> fcm_w, fcm_b;        // per-stack merged fc . res.conv3 weights [256][128] and bias
   uint16_t* d_w = nullptr;
   float* d_a = nullptr;
   unsigned long long* d_keys = nullptr;  // [max_batch][kHeatPad] arg-max keys of the fused score head (zero between forwards)
@@ -487,6 +488,39 @@ struct Emitter {
     return m;
   }
 
+  // fc(conv3(t) + b3 + h) + b_fc = (W_fc W_3) t + W_fc h + (W_fc b3 + b_fc): the residual bottleneck's last conv and the
+  // fc conv behind it have nothing non-linear between them.  Returns the 256 x 128 product (fp64 accumulate, one
+  // rounding to bf16 at packing time) with the combined bias; cached on the handle so the views stay valid.
+  Convp merged_fc(const StackP& s, int i) {
+    if ((int)hg->fcm_w.size() <= i) {
+      hg->fcm_w.resize(i + 1);
+      hg->fcm_b.resize(i + 1);
+    }
+    std::vector<float>& W = hg->fcm_w[i];
+    std::vector<float>& b = hg->fcm_b[i];
+    if (W.empty()) {
+      W.assign((size_t)kCh * kFeats, 0.0f);
+      b.assign(kCh, 0.0f);
+      for (int o = 0; o < kCh; ++o) {
+        double bb = s.fc.bias[o];
+        for (int m = 0; m < kCh; ++m) bb += (double)s.fc.w[(size_t)o * kCh + m] * s.res.c3.bias[m];
+        b[o] = (float)bb;
+        for (int c = 0; c < kFeats; ++c) {
+          double acc = 0.0;
+          for (int m = 0; m < kCh; ++m) acc += (double)s.fc.w[(size_t)o * kCh + m] * s.res.c3.w[(size_t)m * kFeats + c];
+          W[(size_t)o * kFeats + c] = (float)acc;
+        }
+      }
+    }
+    Convp m;
+    m.w = W.data();
+    m.bias = b.data();
+    m.cout = kCh;
+    m.cin = kFeats;
+    m.k = 1;
+    return m;
+  }
+
   static int bn_for(int cout_pad) { return cout_pad >= 256 ? 256 : cout_pad; }
   static double fpp(const Convp& c) { return 2.0 * c.cin * c.cout * c.k * c.k; }
 
@@ -548,6 +582,10 @@ struct Emitter {
     const Tensor* pool_raw = nullptr;
     const Tensor* pool_act = nullptr;
     Affine pool_aff{};
+    // the last ss_k of the K weight columns multiply a second activation tensor (read from shared memory) instead of
+    // the previous stage's output
+    const Tensor* in2 = nullptr;
+    int ss_k = 0;
   };
 
   // the chain kernel pools in its epilogue on 8-wide tiles (halo-mode 8 x 16 tiles, or maps 8 pixels wide)
@@ -599,7 +637,12 @@ struct Emitter {
       ChainStage& st = p.st[i];
       if ((err = make_tmap_wgt(&st.tmB, hg->d_w + s.w_off, s.K, s.N, 64))) return;  // 64 rows: one CTA's half of an N = 128 block
       st.n = s.N;
-      st.kblocks = s.K / 64;
+      st.kblocks = (s.K - s.ss_k) / 64;
+      if (s.ss_k) {
+        st.ss_kblocks = s.ss_k / 64;
+        if ((err = make_tmap_act(&st.tmA2, ptr(*s.in2), s.in2->C, in.W, in.H, B, tw, th, nb))) return;
+        bytes_px += 2.0 * s.ss_k;
+      }
       st.relu1 = s.relu1 ? 1 : 0;
       st.unit_scale = s.unit_scale ? 1 : 0;
       st.scale1 = hg->d_a + s.a1.scale_off;
@@ -792,7 +835,8 @@ struct Emitter {
         conv(t1r, w2, 9, kFeats, kFeats, 128, a2, true, nullptr, &t2, nullptr, nullptr, nullptr, fpp(b.c2));
         tfree(t1r);
       }
-      {
+      const bool fc_merge = hg->fuse >= 2 && !getenv("DF3D_HG_NO_FC_MERGE");
+      if (!fc_merge) {
         StageSpec& q = sp[n++];  // r = conv3 + h (feeds fc raw: fc is conv -> BN -> ReLU)
         q.w_off = pack_weights(b.c3, kCh, kFeats);
         q.K = kFeats;
@@ -806,12 +850,23 @@ struct Emitter {
       Tensor f, nx, t1x;
       {
         StageSpec& q = sp[n++];  // f = relu(bn(fc(r)))
-        q.w_off = pack_weights(s.fc, kCh, kCh);
-        q.K = kCh;
+        if (fc_merge) {
+          // ... with r never formed: (W_fc W_3) t2 from tensor memory + W_fc h from shared memory (see merged_fc)
+          Convp m = merged_fc(s, i);
+          q.w_off = pack_weights_concat(m, s.fc, kCh);
+          q.K = kFeats + kCh;
+          q.ss_k = kCh;
+          q.in2 = &h;
+          q.a1 = conv_affine(m, &s.fc_bn, kCh);
+          q.flop_per_px = fpp(b.c3) + fpp(s.fc);
+        } else {
+          q.w_off = pack_weights(s.fc, kCh, kCh);
+          q.K = kCh;
+          q.a1 = conv_affine(s.fc, &s.fc_bn, kCh);
+          q.flop_per_px = fpp(s.fc);
+        }
         q.N = kCh;
-        q.a1 = conv_affine(s.fc, &s.fc_bn, kCh);
         q.relu1 = true;
-        q.flop_per_px = fpp(s.fc);
         if (last) {
           f = talloc(H4, W4, kCh);
           q.out_raw = &f;

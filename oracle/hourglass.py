@@ -103,10 +103,13 @@ class HourglassNet(nn.Module):
         self.fc_ = nn.ModuleList([nn.Conv2d(ch, ch, 1, bias=True) for _ in range(num_stacks - 1)])
         self.score_ = nn.ModuleList([nn.Conv2d(num_classes, ch, 1, bias=True) for _ in range(num_stacks - 1)])
 
-    def forward(self, x, emulate_bf16=False, gray_fold=None):
+    def forward(self, x, emulate_bf16=False, gray_fold=None, fc_merge=True):
         """gray_fold (emulation only): the CUDA path takes uint8 gray images whose three input planes are
         identical and folds the stem weights over the input channel (fp32 sum, one bf16 rounding);
-        None = do the same whenever the three planes of `x` are identical."""
+        None = do the same whenever the three planes of `x` are identical.
+        fc_merge (emulation only): the CUDA path evaluates fc(res.conv3(t) + h) as (W_fc W_3) t + W_fc h -- the
+        product merged in fp64 and rounded to bf16 once, the sum conv3(t) + h never rounded (DF3D_HG_NO_FC_MERGE=1
+        restores the separate convolutions, fc_merge=False emulates that)."""
         rnd = _bf16 if emulate_bf16 else (lambda t: t)
         wq = (lambda c: _bf16(c.weight)) if emulate_bf16 else (lambda c: c.weight)
         x = rnd(x)
@@ -124,9 +127,20 @@ class HourglassNet(nn.Module):
         out = []
         for i in range(self.num_stacks):
             y = self.hg[i](x, rnd, wq)
-            y = self.res[i][0](y, rnd, wq)
             fc_conv, fc_bn = self.fc[i][0], self.fc[i][1]
-            y = rnd(F.relu(fc_bn(F.conv2d(y, wq(fc_conv), fc_conv.bias))))
+            if emulate_bf16 and fc_merge:
+                rb = self.res[i][0]
+                a = rnd(F.relu(rb.bn1(y)))
+                t1 = rnd(F.relu(rb.bn2(F.conv2d(a, wq(rb.conv1), rb.conv1.bias))))
+                t2 = rnd(F.relu(rb.bn3(F.conv2d(t1, wq(rb.conv2), rb.conv2.bias, padding=1))))
+                Wfc, W3 = fc_conv.weight.double()[:, :, 0, 0], rb.conv3.weight.double()[:, :, 0, 0]
+                Wm = (Wfc @ W3).float()
+                bm = (Wfc @ rb.conv3.bias.double() + fc_conv.bias.double()).float()
+                pre = F.conv2d(t2, _bf16(Wm)[:, :, None, None]) + F.conv2d(y, wq(fc_conv)) + bm.view(1, -1, 1, 1)
+                y = rnd(F.relu(fc_bn(pre)))
+            else:
+                y = self.res[i][0](y, rnd, wq)
+                y = rnd(F.relu(fc_bn(F.conv2d(y, wq(fc_conv), fc_conv.bias))))
             score = F.conv2d(y, wq(self.score[i]), self.score[i].bias)  # fp32, not rounded
             out.append(score)
             if i < self.num_stacks - 1:

@@ -19,7 +19,7 @@ def main(path, tag):
         n, t = tot.get(name, (0, 0.0))
         tot[name] = (n + 1, t + ms)
     total = sum(t for _, t in tot.values())
-    print(f"# {tag}: ncu launch list of ONE full-size bench step (bench.py --profile, NVTX range df3d_step): 256 frames x 7 cams,")
+    print(f"# {tag}: ncu launch list of ONE full-size bench step (bench.py --profile, NVTX range df3d_step): 256 frames x 7 cams (bench.py --profile --frames 256),")
     print("# 8-stack 256x256, conv-chain plan (DF3D_HG_FUSE=2).  ncu --metrics gpu__time_duration.sum --clock-control none")
     print(f"# {sum(n for n, _ in tot.values())} launches, {total:.3f} ms summed (cold-cache, serialised: compare SHARES with bench.py's roofline.share_of_step)")
     print(f"{'kernel':40s} {'launches':>8s} {'ms':>10s} {'share':>8s}")
