@@ -74,16 +74,29 @@ class Core:
 
     def __init__(self, input_folder: str, output_folder: Optional[str] = None, num_images_max: Optional[int] = None,
                  camera_ordering: List[int] = [0, 1, 2, 3, 4, 5, 6], state_dict=None, weights=None, mean=None,
-                 gpu_decode=False):
+                 gpu_decode=False, stream_videos=False):
         """Same four arguments as the reference.  Extra keywords (the reference reads them from its config,
         df3d/config.py:30-39): `weights` = hourglass checkpoint (sh8_deepfly.tar layout) or `state_dict`,
-        `mean` = per-channel mean or the path of a mean.pth.tar, `gpu_decode` = nvJPEG instead of libjpeg."""
+        `mean` = per-channel mean or the path of a mean.pth.tar, `gpu_decode` = nvJPEG instead of libjpeg,
+        `stream_videos` = decode camera_N.mp4 straight into the pipeline instead of expanding them to JPEG files
+        first (opt-in: the reference's frames have been through ffmpeg's MJPEG encoder once more)."""
         self.input_folder = input_folder
         self.output_folder = self.input_folder + "_df3d" if output_folder is None else output_folder
-        self.expand_videos()
-        self.fps = None
+        self._stream_videos = bool(stream_videos)
+        if not self._stream_videos:
+            self.expand_videos()
+        self.fps = self.get_fps()
         self.num_images_max = num_images_max if num_images_max is not None else 0
-        self.max_img_id = get_max_img_id(self.input_folder)
+        video_shape = None
+        if self._stream_videos:
+            from .inference import VideoReader
+
+            with VideoReader(self.input_folder) as vr:
+                if vr.num_frames < 1:
+                    raise FileNotFoundError("No image found.")
+                self.max_img_id, video_shape = vr.num_frames - 1, [vr.shape[1], vr.shape[0]]
+        else:
+            self.max_img_id = get_max_img_id(self.input_folder)
         if self.num_images_max > 0:
             self.num_images = min(self.num_images_max, self.max_img_id + 1)
             self.max_img_id = self.num_images - 1
@@ -91,7 +104,7 @@ class Core:
             self.num_images = self.max_img_id + 1
         image_path = os.path.join(self.input_folder, "camera_{cam_id}_img_{img_id}.jpg")
         image0 = image_path.format(cam_id=0, img_id=0)
-        shape = _read_image_shape(image0) if os.path.exists(image0) else None
+        shape = video_shape if video_shape is not None else (_read_image_shape(image0) if os.path.exists(image0) else None)
         if shape is None:
             raise ValueError(f"Image shape not specified and could not be read from {image0}")
         self.image_shape = shape                       # [W, H], e.g. [960, 480]
@@ -166,7 +179,7 @@ class Core:
             folder=self.input_folder, camera_ids_to_flip=flip, return_heatmap=False, return_confidence=True,
             max_img_id=self.max_img_id, batch_size=batch_size, disable_pin_memory=disable_pin_memory,
             state_dict=self._state_dict, weights=self._weights, mean=self._mean, gpu_decode=self._gpu_decode,
-            stats=self.ingest_stats)
+            stats=self.ingest_stats, source="videos" if self._stream_videos else "images")
         self.conf = conf
         # packing runs on the device from the integer arg-max indices (bit-exact with core.py:187-203)
         Hh, Wh = HEATMAP_SHAPE
@@ -250,12 +263,20 @@ class Core:
         return np.array(camera_ordering)
 
     def expand_videos(self):
-        """camera_x.mp4 -> camera_x_img_y.jpg when the images are missing (core.py:446-459; the
-        reference shells out to ffmpeg, here OpenCV decodes -- ingest is not on the hot path)."""
+        """camera_x.mp4 -> camera_x_img_y.jpg when the images are missing (core.py:446-459).  With ffmpeg on the PATH
+        this is the reference's command, byte for byte (`-qscale:v 2 -start_number 0`); without it OpenCV's bundled
+        FFmpeg decodes and libjpeg writes at quality 95 -- same frames, slightly different JPEG quantisation."""
+        import shutil
+        import subprocess
+
         for vid in glob.glob(os.path.join(self.input_folder, "camera_?.mp4")):
             cam_id = int(re.match(r"camera_(\d+)", os.path.basename(vid))[1])
             if os.path.exists(os.path.join(self.input_folder, f"camera_{cam_id}_img_0.jpg")) or \
                     os.path.exists(os.path.join(self.input_folder, f"camera_{cam_id}_img_000000.jpg")):
+                continue
+            if shutil.which("ffmpeg"):
+                subprocess.call(["ffmpeg", "-nostats", "-loglevel", "error", "-i", vid, "-qscale:v", "2", "-start_number", "0",
+                                 os.path.join(self.input_folder, f"camera_{cam_id}_img_%d.jpg")], stdin=subprocess.DEVNULL)
                 continue
             import cv2
 
@@ -268,6 +289,35 @@ class Core:
                 i += 1
                 ok, frame = cap.read()
             cap.release()
+
+    def get_fps(self):
+        """Frame rate of the input videos (core.py:416-444: ffprobe; OpenCV's container read when ffprobe is absent)."""
+        import shutil
+        import subprocess
+
+        rates = []
+        for vid in sorted(glob.glob(os.path.join(self.input_folder, "camera_?.mp4"))):
+            if shutil.which("ffprobe"):
+                try:
+                    out = subprocess.check_output(["ffprobe", "-v", "error", "-select_streams", "v:0", "-show_entries",
+                                                   "stream=avg_frame_rate", "-of", "default=noprint_wrappers=1:nokey=1", vid], text=True).strip()
+                    num, _, den = out.partition("/")
+                    rates.append(float(num) / float(den) if den and float(den) != 0 else float(num))
+                    continue
+                except Exception:
+                    logger.warning(f"ffprobe failed on {vid}")
+            import cv2
+
+            cap = cv2.VideoCapture(vid)
+            fps = cap.get(cv2.CAP_PROP_FPS)
+            cap.release()
+            if fps and fps > 0:
+                rates.append(float(fps))
+        if not rates:
+            return None
+        if any(abs(r - rates[0]) > 1e-9 for r in rates):
+            logger.warning(f"Framerates of input videos differ from one another, using the first one: {rates}")
+        return rates[0]
 
     def delete_images(self):
         """Deletes camera_N_img_*.jpg for every camera that has a camera_N.mp4 (core.py:461-475)."""

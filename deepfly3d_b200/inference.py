@@ -112,6 +112,61 @@ class FolderReader:
         return [f.result() for f in futures]
 
 
+class VideoReader:
+    """Frame blocks straight from ``camera_{c}.mp4`` (streaming ingest), without the
+    reference's detour through JPEG files (``Core.expand_videos``, df3d/core.py:446-459).  One decode thread per
+    camera (OpenCV's bundled FFmpeg; this image has no NVDEC binding -- no Video Codec SDK headers, PyNvVideoCodec,
+    DALI or torchcodec), frames converted to gray on the host.  Blocks must be requested in order."""
+
+    def __init__(self, folder, workers=None):
+        import cv2
+
+        self.folder = folder
+        self.workers = NUM_CAMERAS
+        self._caps = []
+        for c in range(NUM_CAMERAS):
+            path = os.path.join(folder, f"camera_{c}.mp4")
+            cap = cv2.VideoCapture(path)
+            if not cap.isOpened():
+                raise FileNotFoundError(f"cannot open {path}")
+            self._caps.append(cap)
+        self.num_frames = min(int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) for cap in self._caps)
+        self.shape = (int(self._caps[0].get(cv2.CAP_PROP_FRAME_HEIGHT)), int(self._caps[0].get(cv2.CAP_PROP_FRAME_WIDTH)))
+        self._next = [0] * NUM_CAMERAS
+        self._pool = ThreadPoolExecutor(max_workers=NUM_CAMERAS, thread_name_prefix="df3d-video")
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for cap in self._caps:
+            cap.release()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _read_camera(self, arr, c, t0, t1):
+        import cv2
+
+        if self._next[c] != t0:
+            raise ValueError(f"camera {c}: video blocks must be read in order (next frame {self._next[c]}, asked for {t0})")
+        for t in range(t0, t1):
+            ok, frame = self._caps[c].read()
+            if not ok:
+                raise FileNotFoundError(f"camera_{c}.mp4 ends at frame {t}")
+            arr[c, t - t0] = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
+        self._next[c] = t1
+
+    def read_block_async(self, t0, t1, out):
+        arr = out.numpy()
+        return [self._pool.submit(self._read_camera, arr, c, t0, t1) for c in range(NUM_CAMERAS)]
+
+    @staticmethod
+    def wait(futures):
+        return [f.result() for f in futures]
+
+
 def read_images(folder, max_img_id, pin_memory=True):
     """-> uint8 tensor (7, T, Hs, Ws): the gray frames at their native size in (pinned) host memory.  Whole
     recording at once -- small folders and tests; ``inference_folder`` streams blocks instead."""
@@ -254,12 +309,13 @@ def _jpeg_decoder():
 
 def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return_confidence=True, max_img_id=None,
                      batch_size=8, disable_pin_memory=False, state_dict=None, weights=None, input_size=None,
-                     device="cuda", gpu_decode=False, mean=None, block_frames=None, workers=None, stats=None):
+                     device="cuda", gpu_decode=False, mean=None, block_frames=None, workers=None, stats=None, source="images"):
     """Runs the hourglass on every camera_{0..6}_img_{0..max_img_id}.jpg of `folder`.
 
     batch_size is the reference's DataLoader batch (images per forward).  Here a forward runs over a block of
     frames sized for the GPU (``block_frames_for``); a batch_size above that raises the block.  `stats`, when a
-    dict, receives the block plan and the seconds spent waiting for the host decode."""
+    dict, receives the block plan and the seconds spent waiting for the host decode.  source="videos" streams the
+    frames from camera_{0..6}.mp4 instead of the expanded JPEG files (see VideoReader)."""
     from . import ops
 
     if max_img_id is None:
@@ -284,7 +340,9 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     import time
 
     wait_s = 0.0
-    with torch.cuda.device(dev), FolderReader(folder, workers=workers) as rd:
+    if source not in ("images", "videos") or (source == "videos" and gpu_decode):
+        raise ValueError("source must be 'images' or 'videos' (videos are decoded on the host)")
+    with torch.cuda.device(dev), (VideoReader(folder) if source == "videos" else FolderReader(folder, workers=workers)) as rd:
         main = torch.cuda.current_stream()
         copy_stream = torch.cuda.Stream()
         if gpu_decode:

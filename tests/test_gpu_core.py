@@ -223,3 +223,48 @@ def test_sharded_two_gpus_equals_single_gpu(tmp_path, lib_built):
         assert torch.equal(d["idx"], ref["idx"].cpu().view(7, T, -1)[:, lo:hi].reshape(7 * (hi - lo), -1))
         assert torch.equal(d["cam"], ref["cam_rt"].cpu()), "replicated bundle adjustment differs from the single-GPU solve"
         assert torch.equal(d["x3d"], ref["points3d_wo_procrustes"].cpu())
+
+
+def test_core_streams_videos_without_expanding_them(tmp_path, lib_built):
+    """config 5 ingest: Core(stream_videos=True) decodes camera_N.mp4 straight into the pipeline (no JPEG files are
+    written) and gives what the same decoded frames give through the engine directly."""
+    import cv2
+
+    from deepfly3d_b200 import inference
+    from deepfly3d_b200.core import Core
+    from deepfly3d_b200.hourglass import HourglassEngine
+    from deepfly3d_b200.skeleton import HEATMAP_SHAPE
+
+    d = tmp_path / "sample" / "test"
+    d.mkdir(parents=True)
+    T = 3
+    for c in range(7):
+        vw = cv2.VideoWriter(str(d / f"camera_{c}.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 100.0, (960, 480))
+        if not vw.isOpened():
+            pytest.skip("no mp4 encoder in this OpenCV build")
+        for t in range(T):
+            vw.write(cv2.imread(os.path.join(IMAGES, f"camera_{c}_img_{t}.jpg")))
+        vw.release()
+    model = ohg.make_model(2, seed=0)
+    core = Core(str(d), num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6], state_dict=model.state_dict(), stream_videos=True)
+    assert core.num_images == T and core.image_shape == [960, 480] and abs(core.fps - 100.0) < 1e-6
+    core.pose2d_estimation()
+    assert not [f for f in os.listdir(d) if f.endswith(".jpg")]
+    frames = np.zeros((7, T, 480, 960), dtype=np.uint8)
+    for c in range(7):
+        cap = cv2.VideoCapture(str(d / f"camera_{c}.mp4"))
+        for t in range(T):
+            frames[c, t] = cv2.cvtColor(cap.read()[1], cv2.COLOR_BGR2GRAY)
+    from deepfly3d_b200 import ops
+
+    dev = ops.resize_gray_u8(torch.as_tensor(frames.reshape(7 * T, 480, 960)).cuda(), (256, 512))
+    eng = HourglassEngine(model.state_dict(), 256, 512, max_batch=7 * T)
+    flip = torch.zeros((7, T), dtype=torch.uint8)
+    flip[4:] = 1
+    idx, conf = eng.forward(dev, flip=flip.reshape(-1).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(core.conf.reshape(7 * T, 19), conf.cpu().numpy())
+    ref = opack.pack_points2d(opack.indices_to_points2d(idx.cpu().numpy().reshape(7, T, 19), HEATMAP_SHAPE), range(7))
+    assert np.array_equal(core.points2d, ref)
+    eng.close()
+    inference.drop_engine()

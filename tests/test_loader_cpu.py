@@ -37,3 +37,31 @@ def test_image_name_accepts_zero_padded_ids(tmp_path):
     assert image_name(str(tmp_path), 2, 7).endswith("camera_2_img_000007.jpg")
     (tmp_path / "camera_2_img_7.jpg").write_bytes(b"x")
     assert image_name(str(tmp_path), 2, 7).endswith("camera_2_img_7.jpg")
+
+
+def test_video_reader_streams_frames_in_order(tmp_path):
+    """camera_N.mp4 -> frame blocks (config 5 ingest): camera and frame order, gray conversion, block boundaries."""
+    import torch
+
+    from deepfly3d_b200.inference import VideoReader
+
+    T, H, W = 9, 64, 96
+    for c in range(7):
+        vw = cv2.VideoWriter(str(tmp_path / f"camera_{c}.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 30.0, (W, H))
+        if not vw.isOpened():
+            pytest.skip("no mp4 encoder in this OpenCV build")
+        for t in range(T):
+            vw.write(np.full((H, W, 3), 16 + 32 * c + 3 * t, dtype=np.uint8))
+        vw.release()
+    with VideoReader(str(tmp_path)) as vr:
+        assert vr.num_frames == T and vr.shape == (H, W)
+        buf = torch.zeros((7, 4, H, W), dtype=torch.uint8)
+        seen = np.zeros((7, T))
+        for t0, t1 in [(0, 4), (4, 8), (8, 9)]:
+            vr.wait(vr.read_block_async(t0, t1, buf))
+            seen[:, t0:t1] = buf[:, :t1 - t0].float().mean(dim=(2, 3)).numpy()
+        with pytest.raises(ValueError):
+            vr.wait(vr.read_block_async(3, 4, buf))                        # out of order
+    expect = 16 + 32 * np.arange(7)[:, None] + 3 * np.arange(T)[None, :]
+    assert np.abs(seen - expect).max() <= 3.5                              # lossy codec (limited-range YUV), flat frames
+    assert np.all(np.diff(seen, axis=1) > 0) and np.all(np.diff(seen, axis=0) > 0)   # frame and camera order
