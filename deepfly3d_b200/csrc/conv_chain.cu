@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
-  const int n_chain = p.n_chain;
-  const int head_after = p.head_after;
+  // loop-invariant scalars of the parameter block, pinned in registers: left to itself the compiler re-reads them
+  // from the constant bank inside the per-stage loops, and with a 4.4 KB parameter block those loads miss the
+  // small constant cache (ncu: long-scoreboard / branch-resolving samples on LDCU c[0x0][...] in every role loop)
+  int n_chain = p.n_chain, head_after = p.head_after;
+  asm volatile("" : "+r"(n_chain), "+r"(head_after));
   // CTA pair: rank 0 (the leader) issues every MMA; pair-tile pt = tiles 2 pt (leader) and 2 pt + 1 (peer); a
   // tile past the end is a phantom (its loads are out of bounds = zeros, its stores are skipped)
   const uint32_t rank = cluster_ctarank();
@@ -578,7 +581,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     constexpr uint32_t kNoSlab = 0xffffffffu;
     uint32_t pending = kNoSlab;     // lane 0: slab whose TMA store may still be reading it
     uint32_t spos = 0, sphase = 0;  // ring position / phase of the next residual slab (slab 0 of the next stage with one)
-    const uint32_t n_slabs = (uint32_t)p.n_slabs;
+    uint32_t n_slabs = (uint32_t)p.n_slabs, slab_bytes_r = (uint32_t)p.slab_bytes;
+    int tile_th = p.th, img_B = p.B, img_H = p.H, img_W = p.W;
+    asm volatile("" : "+r"(n_slabs), "+r"(slab_bytes_r), "+r"(tile_th), "+r"(img_B), "+r"(img_H), "+r"(img_W));
     unsigned long long* const dbg = (kProbe && blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
     int di = 4096 * (1 + grp);
     const int dend = di + 4000;
@@ -594,8 +599,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       TilePix tp;
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        tp.inb[w] = (n0 + pn[w]) < p.B && !(kProbe && (p.dbg_exec & 2));
-        tp.pix[w] = (uint32_t)(((n0 + pn[w]) * p.H + (y0 + phh[w])) * p.W + (x0 + pw[w]));
+        tp.inb[w] = (n0 + pn[w]) < img_B && !(kProbe && (p.dbg_exec & 2));
+        tp.pix[w] = (uint32_t)(((n0 + pn[w]) * img_H + (y0 + phh[w])) * img_W + (x0 + pw[w]));
       }
       return tp;
     };
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             sph ^= 1u;
           }
           mbar_wait_warp(sfull(su), sph);
-          slab = s_base + su * (uint32_t)p.slab_bytes;
+          slab = s_base + su * slab_bytes_r;
         }
         EpiRow row[2];
 #pragma unroll
@@ -681,7 +686,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             // from the slab: 8 pooled pixels x 8 sixteen-byte chunks, two items per lane, stored directly (the 8
             // chunks of a pooled pixel are 128 contiguous bytes)
             const uint32_t R0 = 4u * (uint32_t)q;            // first tile row of the quarter
-            const int rows_img = p.th;                         // tile rows per image
+            const int rows_img = tile_th;                      // tile rows per image
             const int qn = n0 + (int)R0 / rows_img, qy = y0 + (int)R0 % rows_img;
             const float* const pc = reinterpret_cast<const float*>(sm + (aff_base - smem_base)) + st.pool_off;
 #pragma unroll
@@ -716,9 +721,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
                 v = ffma2(bf2_unpack(mx.w), make_float2(sb.z, sb.w), make_float2(hb.z, hb.w));
                 act.w = pack2_relu(v.x, v.y);
               }
-              if (qn < p.B && !(kProbe && (p.dbg_exec & 2))) {
+              if (qn < img_B && !(kProbe && (p.dbg_exec & 2))) {
                 const int py = (qy >> 1) + (int)(ppx >> 2), px = (x0 >> 1) + (int)(ppx & 3u);
-                const size_t off = ((((size_t)qn * (p.H >> 1) + py) * (p.W >> 1) + px) * (size_t)st.n + (size_t)cc) * 2;
+                const size_t off = ((((size_t)qn * (img_H >> 1) + py) * (img_W >> 1) + px) * (size_t)st.n + (size_t)cc) * 2;
                 *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.pool_raw) + off) = mx;
                 *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.pool_act) + off) = act;
               }

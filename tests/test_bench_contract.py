@@ -21,7 +21,7 @@ def _latest(pattern):
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    d = _latest("r01?_bench.json")
+    d = _latest("r02?_bench.json")
     assert BASE_KEYS <= set(d)
     assert d["metric"].startswith("7-cam frames/sec") and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert "workload" in d["config"] and "model" not in d["config"]
@@ -33,7 +33,13 @@ def test_committed_bench_line_has_the_contract_keys():
     assert r["traffic"] is None or r["traffic"] > 0
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
-    assert e["h2d_bytes_per_step"] == 7 * 256 * 256 * 256 * d["n_gpus"] and e["d2h_bytes_per_step"] > 0
+    frames = d["config"]["frames_per_gpu"]
+    assert "configs[2]" in d["config"]["workload"] and frames == 1000          # the literal BASELINE.json configuration
+    assert e["h2d_bytes_per_step"] == 7 * frames * 256 * 256 * d["n_gpus"] and e["d2h_bytes_per_step"] > 0
+    assert d["e2e_files"]["value"] > 0 and "Core(folder)" in d["e2e_files"]["path"]   # files on disk -> result pickle
+    assert d["bundle_adjust"]["frames"] == frames * d["n_gpus"]
+    r = d["roofline"]
+    assert abs(r["achieved"] - r["flop_per_launch"] * r["launches_per_step"] / (r["ms_per_launch"] * r["launches_per_step"] / 1e3) / 1e12) < 1e-6 * r["achieved"]
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
@@ -42,7 +48,7 @@ def test_committed_bench_line_has_the_contract_keys():
 
 
 def test_committed_reference_line():
-    d = _latest("r01?_bench_reference.json")
+    d = _latest("r02?_bench_reference.json")
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
