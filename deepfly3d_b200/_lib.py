@@ -12,13 +12,14 @@ DF3D_MAX_CAMS = 8
 
 
 class BAOpts(C.Structure):
-    _fields_ = [("max_iters", C.c_int), ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double)]
+    _fields_ = [("max_iters", C.c_int), ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double), ("solver", C.c_int)]
 
 
 class BAReport(C.Structure):
     _fields_ = [
         ("cost0", C.c_double), ("cost", C.c_double), ("reg", C.c_double),
         ("iters", C.c_int32), ("accepted", C.c_int32), ("n_obs", C.c_int32), ("status", C.c_int32),
+        ("lsmr_itn", C.c_int32), ("lsmr_istop", C.c_int32),
     ]
 
 

@@ -27,6 +27,8 @@
 //                 ratio test, radius update and termination rule, and re-solves the 2-D problem after a
 //                 rejected step
 //   ba_apply    : copies the candidate points after an accepted step
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -34,8 +36,10 @@ namespace df3d {
 
 constexpr int kBAThreads = 128;
 constexpr int kBAWarps = kBAThreads / 32;
-constexpr int kBAMaxBlocks = 148;
+constexpr int kBAMaxBlocks = 4 * 148;  // per-block partials are summed by the last block in block order: bounded, but enough
+                                      // blocks to keep several per SM in flight (the passes are fp64 latency-bound)
 constexpr int kMaxN = 6 * DF3D_MAX_CAMS;
+constexpr int kLsmrRed = kMaxN + 2;  // values of one grid-wide reduction of the LSMR kernel
 
 struct BAState {
   double Delta, F, F0, ftol, xtol, gtol, reg;
@@ -45,7 +49,8 @@ struct BAState {
   double gS0, gS1;        // gradient in that basis
   double coef_g, coef_gn; // step_h = coef_g g_h + coef_gn gn_h
   double pred, sh_norm;   // predicted reduction and |step_h| of the current candidate
-  int iter, accepted, max_iters, done, status, n_obs, accept_flag, need_lin, first, pad;
+  int iter, accepted, max_iters, done, status, n_obs, accept_flag, need_lin, first, solver;
+  int lsmr_itn, lsmr_istop;  // of the last LSMR solve (solver 1)
 };
 
 // ba_gradient's reduction vector
@@ -78,6 +83,12 @@ struct BAWorkspace {  // carved out of the caller's buffer
   double* X_new;           // TJ*3 candidate points
   double* partials;        // kBAMaxBlocks * max(sys_doubles, g_doubles)
   double* red;             // reduced vector of the last reducing kernel
+  // LSMR (solver 1): u lives in residual space, v / h / hbar in the scaled unknown space (point parts; x = gnp)
+  double* lu;              // C*TJ*2
+  double* lv;              // TJ*3
+  double* lh;              // TJ*3
+  double* lhb;             // TJ*3
+  double* lpart;           // 2 * kBAMaxBlocks * kLsmrRed
 };
 
 static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* ws) {
@@ -105,6 +116,11 @@ static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* 
   w.X_new = reinterpret_cast<double*>(take(TJ * 3 * 8));
   w.partials = reinterpret_cast<double*>(take((size_t)kBAMaxBlocks * nred * 8));
   w.red = reinterpret_cast<double*>(take(nred * 8));
+  w.lu = reinterpret_cast<double*>(take((size_t)C * TJ * 2 * 8));
+  w.lv = reinterpret_cast<double*>(take(TJ * 3 * 8));
+  w.lh = reinterpret_cast<double*>(take(TJ * 3 * 8));
+  w.lhb = reinterpret_cast<double*>(take(TJ * 3 * 8));
+  w.lpart = reinterpret_cast<double*>(take((size_t)2 * kBAMaxBlocks * kLsmrRed * 8));
   if (ws) *ws = w;
   return off;
 }
@@ -127,6 +143,7 @@ __global__ void ba_begin_kernel(const double* __restrict__ cam_rt, int C, df3d_b
     s.max_iters = opts.max_iters;
     s.need_lin = 1;
     s.first = 1;
+    s.solver = opts.solver;
     *ws.state = s;
     for (int i = 0; i < 8; ++i) ws.counters[i] = 0u;
   }
@@ -526,7 +543,7 @@ __global__ void __launch_bounds__(kBAThreads)
 ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy,
                 const double* __restrict__ pts3d, int C, int TJ, BAWorkspace ws) {
   extern __shared__ double smem[];
-  if (ws.state->done || !ws.state->need_lin) return;
+  if (ws.state->done || !ws.state->need_lin || ws.state->solver == 1) return;
   const double reg = ws.state->reg;
   const int nsys = sys_doubles(C);
   const int n6 = 6 * C;
@@ -659,7 +676,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(int C, BAWorksp
   __shared__ double rhs[kMaxN], sol[kMaxN], res[kMaxN];
   __shared__ double dsc[kMaxN];
   BAState* st = ws.state;
-  if (st->done || !st->need_lin) return;
+  if (st->done || !st->need_lin || st->solver == 1) return;
   const int n = 6 * C;
   const double reg = st->reg;
   const double* sys = ws.red;
@@ -796,7 +813,10 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
       d[i] = 1.0 / ws.sinv_p[(size_t)g * 3 + i];
       gh[i] = ws.gp[(size_t)g * 3 + i] * d[i];
     }
-    if (mask) {  // pp = (D V D + reg I)^-1 D rp = D^-1 M rp
+    if (st->solver == 1) {  // gn_h comes from the LSMR kernel
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pp[i] = ws.gnp[(size_t)g * 3 + i];
+    } else if (mask) {  // pp = (D V D + reg I)^-1 D rp = D^-1 M rp
       double Mm[3][3];
       point_M(mask, V, JpLast, d, reg, Mm);
 #pragma unroll
@@ -870,6 +890,379 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
   st->gS0 = t00 * gg;
   st->gS1 = t10 * gg + t11 * g_gn;
   solve_subproblem(st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// solver 1: the regularised Gauss-Newton step the way SciPy gets it -- scipy.sparse.linalg.lsmr(J_h, f, damp =
+// sqrt(reg), atol = btol = 1e-6, conlim = 1e8) with x0 = 0 (scipy/sparse/linalg/_isolve/lsmr.py), statement by
+// statement: Golub-Kahan bidiagonalisation with the two plane rotations per step, the same estimates of |r|, |A^T r|,
+// |A|, cond(A), |x| and the same stopping rules, so that the TRUNCATED iterate SciPy stops at is reproduced (its
+// distance to the exact step is what separates the exact solver from the golden file: 5e-5 mm).  J_h is never formed:
+// per observation the 2 x 9 analytic Jacobian is recomputed.  One persistent cooperative kernel per solve; each
+// iteration is three passes over the points with a grid-wide barrier after each (|u|, A^T u + |v|, |x|); every block
+// reduces the per-block partials in the same fixed order, so all blocks carry identical scalars and camera vectors
+// (in shared memory) and take the same branches.  Point vectors live in the workspace (x = gnp).
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ void sym_ortho(double a, double b, double& c, double& s, double& r) {
+  auto sgn = [](double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0); };
+  if (b == 0.0) {
+    c = sgn(a);
+    s = 0.0;
+    r = fabs(a);
+  } else if (a == 0.0) {
+    c = 0.0;
+    s = sgn(b);
+    r = fabs(b);
+  } else if (fabs(b) > fabs(a)) {
+    const double tau = a / b;
+    s = sgn(b) / sqrt(1.0 + tau * tau);
+    c = s * tau;
+    r = b / s;
+  } else {
+    const double tau = b / a;
+    c = sgn(a) / sqrt(1.0 + tau * tau);
+    s = c * tau;
+    r = a / c;
+  }
+}
+
+struct LsmrScalars {
+  double alpha, beta, inv_beta;
+  double zetabar, alphabar, rho, rhobar, cbar, sbar;
+  double betadd, betad, rhodold, tautildeold, thetatilde, zeta, d;
+  double normA2, maxrbar, minrbar, normA, condA, normx, normr, normar, normb;
+  double c_hbar, c_x, c_h;  // coefficients of this iteration's vector updates
+  int itn, istop;
+};
+
+__global__ void __launch_bounds__(kBAThreads)
+ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_xy, const double* __restrict__ pts3d, int C,
+               int TJ, BAWorkspace ws, double atol, double btol, double conlim, int maxiter) {
+  extern __shared__ double smem[];
+  cg::grid_group grid = cg::this_grid();
+  BAState* st = ws.state;
+  if (st->done || !st->need_lin || st->solver != 1) return;  // uniform over the grid
+  const int n6 = 6 * C;
+  double* s_cam = smem;                       // staged cameras
+  double* s_dc = s_cam + C * kCamStride;      // 1 / camera column norms
+  double* s_vc = s_dc + n6;                   // camera parts of v, h, hbar, x (identical in every block)
+  double* s_hc = s_vc + n6;
+  double* s_hbc = s_hc + n6;
+  double* s_xc = s_hbc + n6;
+  double* s_red = s_xc + n6;                  // reduced values [kLsmrRed]
+  double* s_tile = s_red + kLsmrRed;          // per-warp tiles [kBAWarps][kLsmrRed]
+  __shared__ LsmrScalars S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double damp = sqrt(st->reg);
+  if (threadIdx.x < C) stage_camera(ws.cam + threadIdx.x * 6, intr + threadIdx.x * 4, s_cam + threadIdx.x * kCamStride);
+  if (threadIdx.x < n6) {
+    s_dc[threadIdx.x] = 1.0 / ws.sinv_c[threadIdx.x];
+    s_vc[threadIdx.x] = s_hc[threadIdx.x] = s_hbc[threadIdx.x] = s_xc[threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+  int flip = 0;
+  // grid-wide sum of the first n entries of every warp tile -> s_red (same order in every block)
+  auto reduce = [&](int n) {
+    __syncthreads();
+    double* part = ws.lpart + ((size_t)flip * kBAMaxBlocks + blockIdx.x) * kLsmrRed;
+    for (int e = threadIdx.x; e < n; e += kBAThreads) {
+      double acc = s_tile[e];
+#pragma unroll
+      for (int w = 1; w < kBAWarps; ++w) acc += s_tile[w * kLsmrRed + e];
+      part[e] = acc;
+    }
+    __threadfence();
+    grid.sync();
+    const double* all = ws.lpart + (size_t)flip * kBAMaxBlocks * kLsmrRed;
+    for (int e = threadIdx.x; e < n; e += kBAThreads) {
+      double acc = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) acc += all[(size_t)b * kLsmrRed + e];
+      s_red[e] = acc;
+    }
+    for (int e = threadIdx.x; e < kBAWarps * kLsmrRed; e += kBAThreads) s_tile[e] = 0.0;
+    flip ^= 1;
+    __syncthreads();
+  };
+  for (int e = threadIdx.x; e < kBAWarps * kLsmrRed; e += kBAThreads) s_tile[e] = 0.0;
+  __syncthreads();
+  double* my = s_tile + warp * kLsmrRed;
+  const int stride = gridDim.x * kBAThreads;
+
+  // ---- u = b = f (residuals), beta = |b|
+  {
+    double acc = 0.0;
+    for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += stride) {
+      const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
+      for (int c = 0; c < C; ++c) {
+        const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
+        if (xy.x == 0.0 || xy.y == 0.0) continue;
+        double r[2];
+        project_residual(s_cam + c * kCamStride, X, xy.x, xy.y, r);
+        ws.lu[((size_t)c * TJ + g) * 2 + 0] = r[0];
+        ws.lu[((size_t)c * TJ + g) * 2 + 1] = r[1];
+        acc += r[0] * r[0] + r[1] * r[1];
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) my[n6] += acc;
+  }
+  reduce(n6 + 1);
+  if (threadIdx.x == 0) {
+    S.normb = S.beta = sqrt(s_red[n6]);
+    S.inv_beta = S.beta > 0.0 ? 1.0 / S.beta : 0.0;
+    S.alpha = 0.0;
+    S.itn = 0;
+    S.istop = 0;
+  }
+  __syncthreads();
+
+  // one pass "v = A^T (u / beta) - beta v": point parts to ws.lv (not normalised yet), camera sums + |v_p|^2 reduced
+  auto pass_atu = [&](double beta_old) {
+    const double ib = S.inv_beta;
+    for (int base = blockIdx.x * kBAThreads; base < TJ; base += stride) {
+      const int g = base + threadIdx.x;
+      const bool valid = g < TJ;
+      double X[3] = {0, 0, 0}, tp[3] = {0, 0, 0};
+      if (valid) {
+        X[0] = pts3d[(size_t)g * 3 + 0];
+        X[1] = pts3d[(size_t)g * 3 + 1];
+        X[2] = pts3d[(size_t)g * 3 + 2];
+      }
+      for (int c = 0; c < C; ++c) {
+        bool vis = false;
+        double2 xy = make_double2(0.0, 0.0);
+        if (valid) {
+          xy = __ldg(pts_xy + (size_t)c * TJ + g);
+          vis = (xy.x != 0.0) && (xy.y != 0.0);
+        }
+        if (!__any_sync(0xffffffffu, vis)) continue;
+        double tc[6] = {0, 0, 0, 0, 0, 0};
+        if (vis) {
+          double r[2], Jc[2][6], Jp[2][3];
+          project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+          const double u0 = ws.lu[((size_t)c * TJ + g) * 2 + 0] * ib, u1 = ws.lu[((size_t)c * TJ + g) * 2 + 1] * ib;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) tp[j] += Jp[0][j] * u0 + Jp[1][j] * u1;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) tc[i] = Jc[0][i] * u0 + Jc[1][i] * u1;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double v = warp_sum(tc[i]);
+          if (lane == 0) my[c * 6 + i] += v;
+        }
+      }
+      double nv = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double vn = tp[j] / ws.sinv_p[(size_t)g * 3 + j] - beta_old * ws.lv[(size_t)g * 3 + j];
+          ws.lv[(size_t)g * 3 + j] = vn;
+          nv += vn * vn;
+        }
+      }
+      nv = warp_sum(nv);
+      if (lane == 0) my[n6] += nv;
+    }
+    reduce(n6 + 1);
+    if (threadIdx.x < n6) s_vc[threadIdx.x] = s_dc[threadIdx.x] * s_red[threadIdx.x] - beta_old * s_vc[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a2 = s_red[n6];
+      for (int i = 0; i < n6; ++i) a2 += s_vc[i] * s_vc[i];
+      S.alpha = sqrt(a2);
+    }
+    __syncthreads();
+    if (threadIdx.x < n6 && S.alpha > 0.0) s_vc[threadIdx.x] *= 1.0 / S.alpha;
+    __syncthreads();
+  };
+
+  // ---- v = A^T u / alpha ; h = v ; hbar = 0 ; x = 0
+  for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) ws.lv[i] = 0.0;
+  __syncthreads();
+  pass_atu(0.0);
+  {
+    const double ia = S.alpha > 0.0 ? 1.0 / S.alpha : 0.0;
+    for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) {
+      const double v = ws.lv[i] * ia;
+      ws.lv[i] = v;
+      ws.lh[i] = v;
+      ws.lhb[i] = 0.0;
+      ws.gnp[i] = 0.0;
+    }
+    if (threadIdx.x < n6) {
+      s_hc[threadIdx.x] = s_vc[threadIdx.x];
+      s_hbc[threadIdx.x] = 0.0;
+      s_xc[threadIdx.x] = 0.0;
+    }
+  }
+  if (threadIdx.x == 0) {
+    S.zetabar = S.alpha * S.beta;
+    S.alphabar = S.alpha;
+    S.rho = S.rhobar = S.cbar = 1.0;
+    S.sbar = 0.0;
+    S.betadd = S.beta;
+    S.betad = 0.0;
+    S.rhodold = 1.0;
+    S.tautildeold = S.thetatilde = S.zeta = S.d = 0.0;
+    S.normA2 = S.alpha * S.alpha;
+    S.maxrbar = 0.0;
+    S.minrbar = 1e100;
+    S.normA = sqrt(S.normA2);
+    S.condA = 1.0;
+    S.normx = 0.0;
+    S.normr = S.beta;
+    S.normar = S.alpha * S.beta;
+    if (S.normar == 0.0 || S.normb == 0.0) S.istop = -1;  // x = 0 is the answer
+  }
+  __syncthreads();
+  const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
+
+  while (S.istop == 0 && S.itn < maxiter) {
+    // ---- u = A v - alpha u ; beta = |u|
+    {
+      const double alpha = S.alpha, ib = S.inv_beta;
+      double acc = 0.0;
+      for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += stride) {
+        const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
+        double vp[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vp[j] = ws.lv[(size_t)g * 3 + j] / ws.sinv_p[(size_t)g * 3 + j];
+        for (int c = 0; c < C; ++c) {
+          const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
+          if (xy.x == 0.0 || xy.y == 0.0) continue;
+          double r[2], Jc[2][6], Jp[2][3];
+          project_jacobian(s_cam + c * kCamStride, X, xy.x, xy.y, r, Jc, Jp);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            double av = Jp[a][0] * vp[0] + Jp[a][1] * vp[1] + Jp[a][2] * vp[2];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) av += Jc[a][i] * (s_dc[c * 6 + i] * s_vc[c * 6 + i]);
+            const size_t o = ((size_t)c * TJ + g) * 2 + a;
+            const double un = av - alpha * (ws.lu[o] * ib);
+            ws.lu[o] = un;
+            acc += un * un;
+          }
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) my[n6] += acc;
+    }
+    reduce(n6 + 1);
+    if (threadIdx.x == 0) {
+      S.beta = sqrt(s_red[n6]);
+      S.inv_beta = S.beta > 0.0 ? 1.0 / S.beta : 0.0;
+    }
+    __syncthreads();
+    // ---- v = A^T u - beta v ; alpha = |v|
+    if (S.beta > 0.0) pass_atu(S.beta);
+    // ---- rotations and estimates (every block, identical inputs)
+    if (threadIdx.x == 0) {
+      S.itn += 1;
+      const double alpha = S.alpha, beta = S.beta;
+      double chat, shat, alphahat, c, s, rho;
+      sym_ortho(S.alphabar, damp, chat, shat, alphahat);
+      const double rhoold = S.rho;
+      sym_ortho(alphahat, beta, c, s, rho);
+      const double thetanew = s * alpha;
+      S.alphabar = c * alpha;
+      const double rhobarold = S.rhobar, zetaold = S.zeta;
+      const double thetabar = S.sbar * rho, rhotemp = S.cbar * rho;
+      double cbar, sbar, rhobar;
+      sym_ortho(S.cbar * rho, thetanew, cbar, sbar, rhobar);
+      S.cbar = cbar;
+      S.sbar = sbar;
+      S.rhobar = rhobar;
+      S.rho = rho;
+      S.zeta = cbar * S.zetabar;
+      S.zetabar = -sbar * S.zetabar;
+      S.c_hbar = -(thetabar * rho / (rhoold * rhobarold));
+      S.c_x = S.zeta / (rho * rhobar);
+      S.c_h = -(thetanew / rho);
+      // estimate of |r|
+      const double betaacute = chat * S.betadd, betacheck = -shat * S.betadd;
+      const double betahat = c * betaacute;
+      S.betadd = -s * betaacute;
+      const double thetatildeold = S.thetatilde;
+      double ctildeold, stildeold, rhotildeold;
+      sym_ortho(S.rhodold, thetabar, ctildeold, stildeold, rhotildeold);
+      S.thetatilde = stildeold * rhobar;
+      S.rhodold = ctildeold * rhobar;
+      S.betad = -stildeold * S.betad + ctildeold * betahat;
+      S.tautildeold = (zetaold - thetatildeold * S.tautildeold) / rhotildeold;
+      const double taud = (S.zeta - S.thetatilde * S.tautildeold) / S.rhodold;
+      S.d = S.d + betacheck * betacheck;
+      S.normr = sqrt(S.d + (S.betad - taud) * (S.betad - taud) + S.betadd * S.betadd);
+      // |A|, cond(A)
+      S.normA2 = S.normA2 + beta * beta;
+      S.normA = sqrt(S.normA2);
+      S.normA2 = S.normA2 + alpha * alpha;
+      S.maxrbar = fmax(S.maxrbar, rhobarold);
+      if (S.itn > 1) S.minrbar = fmin(S.minrbar, rhobarold);
+      S.condA = fmax(S.maxrbar, rhotemp) / fmin(S.minrbar, rhotemp);
+      S.normar = fabs(S.zetabar);
+    }
+    __syncthreads();
+    // ---- hbar = h + c_hbar hbar ; x += c_x hbar ; h = v + c_h h ; |x|
+    {
+      const double chb = S.c_hbar, cx = S.c_x, ch = S.c_h;
+      const double ia = (S.beta > 0.0 && S.alpha > 0.0) ? 1.0 / S.alpha : 1.0;
+      double acc = 0.0;
+      for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) {
+        const double v = S.beta > 0.0 ? ws.lv[i] * ia : ws.lv[i];
+        if (S.beta > 0.0) ws.lv[i] = v;
+        const double h = ws.lh[i];
+        const double hb = ws.lhb[i] * chb + h;
+        const double x = ws.gnp[i] + cx * hb;
+        ws.lhb[i] = hb;
+        ws.gnp[i] = x;
+        ws.lh[i] = h * ch + v;
+        acc += x * x;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) my[n6] += acc;
+      if (threadIdx.x < n6) {
+        const int i = threadIdx.x;
+        const double hb = s_hbc[i] * chb + s_hc[i];
+        s_hbc[i] = hb;
+        s_xc[i] += cx * hb;
+        s_hc[i] = s_hc[i] * ch + s_vc[i];
+      }
+    }
+    reduce(n6 + 1);
+    if (threadIdx.x == 0) {
+      double x2 = s_red[n6];
+      for (int i = 0; i < n6; ++i) x2 += s_xc[i] * s_xc[i];
+      S.normx = sqrt(x2);
+      const double test1 = S.normr / S.normb;
+      const double test2 = (S.normA * S.normr) != 0.0 ? S.normar / (S.normA * S.normr) : INFINITY;
+      const double test3 = 1.0 / S.condA;
+      const double t1 = test1 / (1.0 + S.normA * S.normx / S.normb);
+      const double rtol = btol + atol * S.normA * S.normx / S.normb;
+      int istop = 0;
+      if (S.itn >= maxiter) istop = 7;
+      if (1.0 + test3 <= 1.0) istop = 6;
+      if (1.0 + test2 <= 1.0) istop = 5;
+      if (1.0 + t1 <= 1.0) istop = 4;
+      if (test3 <= ctol) istop = 3;
+      if (test2 <= atol) istop = 2;
+      if (test1 <= rtol) istop = 1;
+      S.istop = istop;
+    }
+    __syncthreads();
+  }
+  // ---- result: camera part of gn_h (point part is ws.gnp already)
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < n6) {
+      ws.gnc[threadIdx.x] = s_xc[threadIdx.x];
+      ws.dcn[threadIdx.x] = s_dc[threadIdx.x] * s_xc[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+      st->lsmr_itn = S.itn;
+      st->lsmr_istop = S.istop;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -989,6 +1382,8 @@ __global__ void ba_end_kernel(double* __restrict__ cam_rt, int C, BAWorkspace ws
     report->accepted = s.accepted;
     report->n_obs = s.n_obs;
     report->status = s.status;
+    report->lsmr_itn = s.lsmr_itn;
+    report->lsmr_istop = s.lsmr_istop;
   }
 }
 
@@ -1037,7 +1432,8 @@ extern "C" size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J) {
 
 extern "C" int df3d_bundle_adjust_launches(const df3d_ba_opts* opts) {
   const int iters = opts ? opts->max_iters : 20;
-  return 2 + 6 * iters;
+  const int per_iter = (opts && opts->solver == 0) ? 6 : 5;  // gradient, (schur, solve | lsmr), backsub, step, apply
+  return 2 + per_iter * iters;
 }
 
 extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double* pts_xy_dev,
@@ -1052,10 +1448,11 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
   BAWorkspace ws;
   const size_t need = ba_workspace_layout(C, T, J, static_cast<char*>(workspace_dev), &ws);
   DF3D_REQUIRE(workspace_bytes >= need, DF3D_ENOMEM, "df3d_bundle_adjust: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-  df3d_ba_opts o{20, 1e-4, 1e-8, 1e-8};
+  df3d_ba_opts o{20, 1e-4, 1e-8, 1e-8, 1};
   if (opts) o = *opts;
-  DF3D_REQUIRE(o.max_iters >= 1 && o.max_iters <= 1000 && o.ftol >= 0.0 && o.xtol >= 0.0 && o.gtol >= 0.0, DF3D_EINVAL,
-               "df3d_bundle_adjust: bad options (max_iters in [1,1000], tolerances >= 0)");
+  DF3D_REQUIRE(o.max_iters >= 1 && o.max_iters <= 1000 && o.ftol >= 0.0 && o.xtol >= 0.0 && o.gtol >= 0.0 &&
+                   (o.solver == 0 || o.solver == 1),
+               DF3D_EINVAL, "df3d_bundle_adjust: bad options (max_iters in [1,1000], tolerances >= 0, solver 0 or 1)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int TJ = T * J;
   const int grid = ba_grid(TJ);
@@ -1065,6 +1462,20 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
   const size_t smem_e = ((size_t)C * kCamStride + 6 * C + kBAWarps * 3) * sizeof(double);
   DF3D_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
   const double2* xy = reinterpret_cast<const double2*>(pts_xy_dev);
+  // solver 1 (LSMR like SciPy): a persistent cooperative kernel, every block resident at once
+  const size_t smem_l = ((size_t)C * kCamStride + 5 * 6 * C + kLsmrRed + kBAWarps * kLsmrRed) * sizeof(double);
+  int lsmr_grid = grid;
+  double lsmr_tol = 1e-6, lsmr_conlim = 1e8;
+  long long lsmr_rows = 2ll * C * TJ, lsmr_cols = 6ll * C + 3ll * TJ;
+  int lsmr_maxiter = (int)(lsmr_rows < lsmr_cols ? lsmr_rows : lsmr_cols);
+  if (o.solver == 1) {
+    int dev = 0, sms = 0, per_sm = 0;
+    DF3D_CUDA(cudaGetDevice(&dev));
+    DF3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DF3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_lsmr_kernel, kBAThreads, smem_l));
+    DF3D_REQUIRE(per_sm >= 1, DF3D_EUNSUPPORTED, "df3d_bundle_adjust: the LSMR kernel does not fit on this device");
+    if (lsmr_grid > per_sm * sms) lsmr_grid = per_sm * sms;
+  }
   ba_begin_kernel<<<1, 64, 0, s>>>(cam_rt_dev, C, o, ws);
   DF3D_LAUNCH_CHECK("ba_begin_kernel");
   const int n3 = TJ * 3;
@@ -1073,8 +1484,14 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
   // fixed launch sequence; kernels become no-ops once the device-side state says `done`
   for (int it = 0; it < o.max_iters; ++it) {
     ba_gradient_kernel<<<grid, kBAThreads, smem_g, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
-    ba_schur_kernel<<<grid, kBAThreads, smem_s, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
-    ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
+    if (o.solver == 1) {
+      void* args[] = {(void*)&intr_dev, (void*)&xy, (void*)&pts3d_dev, (void*)&C, (void*)&TJ, (void*)&ws, (void*)&lsmr_tol,
+                      (void*)&lsmr_tol, (void*)&lsmr_conlim, (void*)&lsmr_maxiter};
+      DF3D_CUDA(cudaLaunchCooperativeKernel((const void*)ba_lsmr_kernel, dim3(lsmr_grid), dim3(kBAThreads), args, smem_l, s));
+    } else {
+      ba_schur_kernel<<<grid, kBAThreads, smem_s, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+      ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
+    }
     ba_backsub_kernel<<<grid, kBAThreads, smem_b, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
     ba_step_kernel<<<grid, kBAThreads, smem_e, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
     ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, it + 1, ws, pts3d_dev);

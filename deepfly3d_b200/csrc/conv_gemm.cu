@@ -40,6 +40,9 @@ constexpr int kMaxResSlots = 4;
 constexpr int kAffBytes = 4 * 256 * 4;  // scale1, shift1, scale2, shift2 for up to 256 channels
 constexpr int kBarBytes = 512;
 constexpr int kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
+constexpr int kHalo9Pitch = 10;                          // halo row of an 8-wide tile
+constexpr int kHalo9Bytes = 18 * kHalo9Pitch * 128;      // (16 + 2) x (8 + 2) pixels x 64 channels
+constexpr int kHalo9Slot = 23552;                        // ... padded to a multiple of 1024 (swizzle atom alignment)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -61,8 +64,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const bool has_res = n_res > 0, has_raw = p.out_raw != nullptr, has_act = p.out_act != nullptr || pool2;
   const bool has_res2 = has_res && p.has_res2 != 0;
   const uint32_t res_slot_bytes = kSlabBytes + (has_res2 ? kHalfSlabBytes : 0);
-  // carve-up: [A/B ring][residual ring][raw out x2][act out x2][affine][barriers]
-  const uint32_t res_base = smem_base + n_stages * kStageBytes;
+  // carve-up: [A/B ring | nine resident weight tiles + halo ring][residual ring][raw out x2][act out x2][affine][barriers]
+  const bool halo9 = p.halo9 != 0;
+  const uint32_t halo_ring = smem_base + 9u * kBBytes;
+  const uint32_t res_base = halo9 ? halo_ring + n_stages * kHalo9Slot : smem_base + n_stages * kStageBytes;
   const uint32_t raw_base = res_base + n_res * res_slot_bytes;
   const uint32_t act_base = raw_base + (has_raw ? 2 * kSlabBytes : 0);
   const uint32_t aff_base = act_base + (has_act ? 2 * kSlabBytes : 0);
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
   auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + kMaxResSlots + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kMaxResSlots);
+  const uint32_t wfull_bar = tmem_slot + 8u;  // halo9: the resident weights have landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -106,6 +112,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(rfull_bar(s), 1);
       mbar_init(rempty_bar(s), 4);
     }
+    mbar_init(wfull_bar, 1);
+    if (halo9) prefetch_tensormap(&p.tmHalo);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -144,7 +152,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A/B producer
-    if (lane == 0) {
+    if (lane == 0 && halo9) {
+      mbar_arrive_expect_tx(wfull_bar, 9u * kBBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_base + tap * kBBytes, &p.tmB, wfull_bar, tap * 64, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int nt, x0, y0, n0;
+        decode_tile(tile, nt, x0, y0, n0);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kHalo9Bytes);
+        tma_load_4d(halo_ring + stage * kHalo9Slot, &p.tmHalo, full_bar(stage), 0, x0 - 1, y0 - 1, n0);
+        if (++stage == (uint32_t)n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    } else if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int nt, x0, y0, n0;
@@ -178,6 +201,37 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       const uint64_t desc_hi = umma_smem_desc_sw128(0);
       uint32_t stage = 0, phase = 0, it = 0;
+      if (halo9) {
+        // A operand of tap (dy, dx) = the halo rows shifted by dy * 10 + dx: 8-row groups 1280 B apart starting at a
+        // row offset (the 128B swizzle is a function of the absolute shared-memory address, which is what TMA wrote)
+        const uint64_t desc_halo = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((kHalo9Pitch * 128) >> 4) << 32);
+        mbar_wait_warp(wfull_bar, 0u);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+          mbar_wait_warp(tempty_bar(as), aphase ^ 1u);
+          mbar_wait_warp(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          const uint32_t hbase = halo_ring + stage * kHalo9Slot;
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_ad = hbase + (uint32_t)((tap / 3) * kHalo9Pitch + tap % 3) * 128u;
+              const uint64_t adesc = desc_halo | (uint64_t)((a_ad >> 4) & 0x3FFFu);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((smem_base + tap * kBBytes) >> 4) & 0x3FFFu);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            umma_commit(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait_warp(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
@@ -607,6 +661,16 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
   const int res_slot = kSlabBytes + (p.has_res2 ? kHalfSlabBytes : 0);
   int n_res = p.residual ? kMaxResSlots : 0;
   int n_stages = 0;
+  if (p.halo9) {
+    DF3D_REQUIRE(p.taps == 9 && p.kc_per_tap == 1 && BN == 64 && p.n_tiles_n == 1 && p.tw == 8 && p.th == 16 && p.nb == 1 &&
+                     p.kb_split == 0,
+                 DF3D_EUNSUPPORTED, "launch_conv_gemm: halo mode needs a 3x3 conv with 64 input and output channels on 8 x 16 tiles");
+    for (;; --n_res) {
+      n_stages = (kSmemLimit - fixed - n_res * res_slot - 9 * BN * 128) / kHalo9Slot;
+      if (n_stages >= 2 || n_res <= (p.residual ? 1 : 0)) break;
+    }
+    if (n_stages > 4) n_stages = 4;
+  } else
   for (;; --n_res) {
     n_stages = (kSmemLimit - fixed - n_res * res_slot) / stage_bytes;
     if (n_stages >= 2 || n_res <= (p.residual ? 1 : 0)) break;
@@ -619,7 +683,7 @@ int launch_conv_gemm(const ConvParams& p_in, int BN, int num_sms, cudaStream_t s
   DF3D_REQUIRE(n_stages >= 2, DF3D_EUNSUPPORTED, "launch_conv_gemm: shared-memory budget too small for BN=%d", BN);
   p.n_stages = n_stages;
   p.n_res_slots = n_res;
-  const int smem = n_stages * stage_bytes + n_res * res_slot + fixed;
+  const int smem = (p.halo9 ? 9 * BN * 128 + n_stages * kHalo9Slot : n_stages * stage_bytes) + n_res * res_slot + fixed;
   const int grid = total < num_sms ? total : num_sms;
   switch (BN) {
     case 32: conv_gemm_kernel<32><<<grid, kConvThreads, smem, stream>>>(p); break;

@@ -30,6 +30,12 @@ struct ConvParams {
   // (64, tw/2, th/2, nb) of the (C, W/2, H/2, N) tensors.  Needs out_raw (its tensor map is not used), nb == 1.
   CUtensorMap tmPoolRaw, tmPoolAct;
   int pool2;
+  // halo9 != 0 (3x3 conv, 64 input channels, BN = 64, 8 x 16 tiles): the nine taps are row-shifted UMMA views of ONE
+  // TMA-loaded (tw + 2) x (th + 2) halo tile (tmHalo) and the nine 64 x 64 weight tiles stay resident in shared
+  // memory -- an N = 64 shared-memory MMA reads 6 KB per 32 clocks, so with nine A boxes + nine weight tiles
+  // streamed per tile the 128 B/clk shared-memory port was the bound (432 KB per tile; 239 KB this way)
+  CUtensorMap tmHalo;
+  int halo9;
   int n_stages;       // A/B ring depth (filled by launch_conv_gemm from the shared-memory budget)
   int n_res_slots;    // residual ring depth (0 without residual)
   int taps;         // 1 (1x1) or 9 (3x3)

@@ -397,6 +397,16 @@ struct Emitter {
     memset(&p, 0, sizeof(p));
     int tw, th, nb;
     tile_geometry(in.H, in.W, &tw, &th, &nb);
+    // 3x3 convs with 64 channels in and out (layer1 / layer2 of the front section): halo mode of conv_gemm
+    const bool halo9 = taps == 9 && CinPad == 64 && CoutPad == 64 && BN == 64 && in.H % 16 == 0 && in.W % 8 == 0 &&
+                       !(residual && residual->valid) && !getenv("DF3D_HG_NO_HALO");
+    if (halo9) {
+      tw = 8;
+      th = 16;
+      nb = 1;
+      p.halo9 = 1;
+      if ((err = make_tmap_box(&p.tmHalo, ptr(in), in.C, in.W, in.H, B, tw + 2, th + 2, 1))) return;
+    }
     op.nb = nb;
     if ((err = make_tmap_act(&p.tmA, ptr(in), in.C, in.W, in.H, B, tw, th, nb))) return;
     if ((err = make_tmap_wgt(&p.tmB, hg->d_w + w_off, taps * CinPad, CoutPad, BN))) return;

@@ -161,10 +161,10 @@ def _decode_report(rep_bytes):
     raw = rep_bytes.cpu().numpy().tobytes()
     r = _lib.BAReport.from_buffer_copy(raw)
     return {"cost0": r.cost0, "cost": r.cost, "reg": r.reg, "iters": r.iters,
-            "accepted": r.accepted, "n_obs": r.n_obs, "status": r.status}
+            "accepted": r.accepted, "n_obs": r.n_obs, "status": r.status, "lsmr_itn": r.lsmr_itn, "lsmr_istop": r.lsmr_istop}
 
 
-def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e-8, gtol=1e-8, workspace=None):
+def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e-8, gtol=1e-8, workspace=None, solver="lsmr"):
     """In-place bundle adjustment (SciPy's trust-region-reflective iteration, see csrc/bundle_adjust.cu).
     cam_rt (C,6) and pts3d (T,J,3) are updated.
 
@@ -178,7 +178,9 @@ def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e
     Cn, T, J, _ = pts_xy.shape
     ws = workspace if workspace is not None else ba_workspace(Cn, T, J, cam_rt.device)
     wp, wn = _aligned_ptr(ws)
-    opts = _lib.BAOpts(int(max_iters), float(ftol), float(xtol), float(gtol))
+    if solver not in ("lsmr", "exact"):
+        raise ValueError("solver must be 'lsmr' (SciPy's truncated LSMR step) or 'exact' (Schur-complement solve)")
+    opts = _lib.BAOpts(int(max_iters), float(ftol), float(xtol), float(gtol), 1 if solver == "lsmr" else 0)
     rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
     check(lib.df3d_bundle_adjust(_ptr(cam_rt), _ptr(intr4), _ptr(pts_xy), Cn, T, J, C.byref(opts), _ptr(pts3d),
                                  _ptr(rep), wp, wn, _stream()))
@@ -186,7 +188,7 @@ def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e
 
 
 def bundle_adjust_launches(max_iters):
-    opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8)
+    opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8, 1)
     return int(lib.df3d_bundle_adjust_launches(C.byref(opts)))
 
 

@@ -133,6 +133,9 @@ typedef struct df3d_ba_opts {
   double ftol;        /* stop when dF < ftol * F and ratio > 0.25  (reference: 1e-4)          */
   double xtol;        /* stop when |dx| < xtol * (xtol + |x|)      (SciPy default 1e-8)       */
   double gtol;        /* stop when |g|_inf < gtol                  (SciPy default 1e-8)       */
+  int solver;         /* regularised Gauss-Newton step: 1 = LSMR with SciPy's tolerances and stopping rules
+                         (reproduces the truncated iterate SciPy stops at; default), 0 = exact Schur-complement
+                         solve (what LSMR converges to; 1-5e-5 mm away on the 3-D joints)        */
 } df3d_ba_opts;
 
 typedef struct df3d_ba_report {   /* written to DEVICE memory (no host sync) */
@@ -143,6 +146,8 @@ typedef struct df3d_ba_report {   /* written to DEVICE memory (no host sync) */
   int32_t accepted;   /* accepted steps            */
   int32_t n_obs;      /* observations used         */
   int32_t status;     /* SciPy's codes: 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol, 0 max_iters */
+  int32_t lsmr_itn;   /* solver 1: iterations and stop code of the last LSMR solve              */
+  int32_t lsmr_istop;
 } df3d_ba_report;
 
 size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J);
@@ -152,7 +157,8 @@ size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J);
  *   pts_xy_dev : (C,T,J,2) pixel (x,y), visibility rule as in df3d_triangulate_dlt
  *   pts3d_dev  : (T,J,3) in: initial points (DLT with the initial cameras), out: BA points
  *   report_dev : df3d_ba_report in device memory (may be NULL)
- * Fixed launch sequence (2 + 6 * max_iters kernels, no host synchronisation); every reduction runs in a
+ * Fixed launch sequence (2 + 6 * max_iters kernels; solver 1: 2 + 5 * max_iters, one of them a persistent
+ * cooperative kernel; no host synchronisation); every reduction runs in a
  * fixed order, so the result is bit-reproducible -- frame-sharded multi-GPU runs all-gather the 2-D points and
  * run this solver replicated, every rank ends with identical cameras. */
 int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double* pts_xy_dev,
