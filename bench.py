@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4], help="BASELINE.json configs[] workload (see the docstring)")
     ap.add_argument("--frames", type=int, default=None, help="override the frames per rank and step (config 4: in total)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames of the CPU hourglass sample (x7 images, batch 8)")
+    ap.add_argument("--ba-solver", default="exact", choices=["exact", "lsmr"],
+                    help="regularised Gauss-Newton step of the bundle adjustment: exact Schur solve (default here: the one that "
+                         "scales to the 8-GPU weak-scaling problem) or SciPy's truncated LSMR (the default of the drop-in Core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the Core-from-JPEG-folder end-to-end leg")
     ap.add_argument("--profile", action="store_true",
@@ -374,7 +377,7 @@ def run_b200(args):
     T, scaling = frames_for(args, world)
     n_img = CAMS * T
     pipe = Pose3DPipeline(random_state_dict(NUM_STACKS, seed=0), IN_H, IN_W, n_img, image_shape=[IN_W, IN_H],
-                          device=dev, ba_max_iters=10, ba_max_frames=1000 if args.config == 4 else None)
+                          device=dev, ba_max_iters=10, ba_max_frames=1000 if args.config == 4 else None, ba_solver=args.ba_solver)
     images = synthetic_images(T, IN_H, IN_W, seed=1 + rank, device=dev)      # resident in HBM
     host_images = torch.empty((n_img, IN_H, IN_W), dtype=torch.uint8).pin_memory()
     host_images.copy_(images)
@@ -486,6 +489,21 @@ def run_b200(args):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
     rep = ops.ba_report(step_resident()["ba_report"]) if full3d else None
+    ba_ms = None
+    if full3d and rank == 0 and world == 1:      # device time of the 2D->3D tail on this step's data, both solvers
+        ba_ms = {}
+        out = step_resident()
+        for solver in ("exact", "lsmr"):
+            cam = pipe.cam_rt0.clone()
+            P0, _ = ops.projection_matrices(cam, pipe.intr4)
+            X0 = ops.triangulate_dlt(P0, out["pts_xy"])
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            ops.bundle_adjust(cam, pipe.intr4, out["pts_xy"], X0, max_iters=pipe.ba_max_iters, ftol=pipe.ba_ftol, solver=solver)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ba_ms[solver] = ev[0].elapsed_time(ev[1])
 
     frames_total = T * world * args.steps
     value = frames_total / (ms_res / 1e3)
@@ -521,7 +539,8 @@ def run_b200(args):
     }
     if rep is not None:
         line["bundle_adjust"] = {"frames": min(T * world, pipe.ba_max_frames or T * world), "observations": rep["n_obs"],
-                                 "evaluations": rep["iters"], "accepted": rep["accepted"], "status": rep["status"]}
+                                 "evaluations": rep["iters"], "accepted": rep["accepted"], "status": rep["status"],
+                                 "solver": args.ba_solver, "device_ms_by_solver": ba_ms}
     if rank == 0:
         if world == 1 and not args.no_files:
             try:

@@ -120,7 +120,10 @@ class CameraNetwork:
         self.points3d = X.cpu().numpy()
         return self.points3d
 
-    def bundle_adjust(self, update_intrinsic=False, update_distort=False, max_iters=20, ftol=1e-4):
+    def bundle_adjust(self, update_intrinsic=False, update_distort=False, max_iters=20, ftol=1e-4, solver="lsmr"):
+        """solver="lsmr" (default) reproduces the truncated LSMR step of the SciPy solver pyba calls and meets the
+        reference test's own tolerances (tests/test_df3d.py:225-240); solver="exact" solves the same regularised
+        Gauss-Newton step exactly (1-5e-5 mm away on the joints, ~4x faster)."""
         if update_intrinsic or update_distort:
             raise NotImplementedError(
                 "only the reference's call bundle_adjust(update_intrinsic=False, update_distort=False) "
@@ -130,7 +133,7 @@ class CameraNetwork:
         intr4 = self._intr4()
         P0, _ = ops.projection_matrices(cam, intr4)
         X = ops.triangulate_dlt(P0, self._pts_xy)
-        rep = ops.bundle_adjust(cam, intr4, self._pts_xy, X, max_iters=max_iters, ftol=ftol)
+        rep = ops.bundle_adjust(cam, intr4, self._pts_xy, X, max_iters=max_iters, ftol=ftol, solver=solver)
         _, R = ops.projection_matrices(cam, intr4)
         cam_h, cam0_h, R_h = cam.cpu().numpy(), cam0.cpu().numpy(), R.cpu().numpy()
         for c, camera in enumerate(self.cam_list):

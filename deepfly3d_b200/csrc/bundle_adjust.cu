@@ -39,7 +39,7 @@ constexpr int kBAWarps = kBAThreads / 32;
 constexpr int kBAMaxBlocks = 4 * 148;  // per-block partials are summed by the last block in block order: bounded, but enough
                                       // blocks to keep several per SM in flight (the passes are fp64 latency-bound)
 constexpr int kMaxN = 6 * DF3D_MAX_CAMS;
-constexpr int kLsmrRed = kMaxN + 2;  // values of one grid-wide reduction of the LSMR kernel
+constexpr int kLsmrRed = 64;  // values of one grid-wide reduction of the LSMR kernel (2 scalars + 6 C camera sums, padded)
 
 struct BAState {
   double Delta, F, F0, ftol, xtol, gtol, reg;
@@ -962,7 +962,11 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
   }
   __syncthreads();
   int flip = 0;
-  // grid-wide sum of the first n entries of every warp tile -> s_red (same order in every block)
+  // Grid-wide sum of entries [0, n) of the warp tiles -> s_red, in an order that is the same in every block: block
+  // partial = tiles in warp order; after the grid barrier warp w of every block adds the blocks b = w, w + 4, ... (lane l
+  // takes entries l and l + 32: the 43 values of a block are consecutive doubles), the four warp sums are added in
+  // warp order.  Partials of other SMs are read through L2 (__ldcg); two buffers alternate so that a block that is
+  // still reading the previous reduction is never overwritten.
   auto reduce = [&](int n) {
     __syncthreads();
     double* part = ws.lpart + ((size_t)flip * kBAMaxBlocks + blockIdx.x) * kLsmrRed;
@@ -975,11 +979,38 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
     __threadfence();
     grid.sync();
     const double* all = ws.lpart + (size_t)flip * kBAMaxBlocks * kLsmrRed;
+    if (n <= 2) {
+      // two scalars: thread t adds the blocks t, t + 128, ... (independent L2 loads), then the 32 lanes of a warp are
+      // added in lane order by a shuffle tree (fixed shape) and the four warps in warp order below
+      double a0 = 0.0, a1 = 0.0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += kBAThreads) {
+        a0 += __ldcg(all + (size_t)b * kLsmrRed);
+        a1 += __ldcg(all + (size_t)b * kLsmrRed + 1);
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane == 0) {
+        s_tile[warp * kLsmrRed] = a0;
+        s_tile[warp * kLsmrRed + 1] = a1;
+      }
+    } else {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+      for (unsigned b = warp; b < gridDim.x; b += kBAWarps) {
+        if (lane < n) a0 += __ldcg(all + (size_t)b * kLsmrRed + lane);
+        if (lane + 32 < n) a1 += __ldcg(all + (size_t)b * kLsmrRed + lane + 32);
+      }
+      s_tile[warp * kLsmrRed + lane] = a0;        // the tiles are free: their content went into `part`
+      if (lane + 32 < kLsmrRed) s_tile[warp * kLsmrRed + lane + 32] = a1;
+    }
+    __syncthreads();
     for (int e = threadIdx.x; e < n; e += kBAThreads) {
-      double acc = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) acc += all[(size_t)b * kLsmrRed + e];
+      double acc = s_tile[e];
+#pragma unroll
+      for (int w = 1; w < kBAWarps; ++w) acc += s_tile[w * kLsmrRed + e];
       s_red[e] = acc;
     }
+    __syncthreads();
     for (int e = threadIdx.x; e < kBAWarps * kLsmrRed; e += kBAThreads) s_tile[e] = 0.0;
     flip ^= 1;
     __syncthreads();
@@ -988,6 +1019,8 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
   __syncthreads();
   double* my = s_tile + warp * kLsmrRed;
   const int stride = gridDim.x * kBAThreads;
+  // reduction slots: [0] |u|^2 or |v_p|^2, [1] |x_p|^2, [2, 2 + 6C) camera sums of A^T u
+  constexpr int kCamSlot = 2;
 
   // ---- u = b = f (residuals), beta = |b|
   {
@@ -1005,11 +1038,11 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
       }
     }
     acc = warp_sum(acc);
-    if (lane == 0) my[n6] += acc;
+    if (lane == 0) my[0] += acc;
   }
-  reduce(n6 + 1);
+  reduce(1);
   if (threadIdx.x == 0) {
-    S.normb = S.beta = sqrt(s_red[n6]);
+    S.normb = S.beta = sqrt(s_red[0]);
     S.inv_beta = S.beta > 0.0 ? 1.0 / S.beta : 0.0;
     S.alpha = 0.0;
     S.itn = 0;
@@ -1050,26 +1083,27 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const double v = warp_sum(tc[i]);
-          if (lane == 0) my[c * 6 + i] += v;
+          if (lane == 0) my[kCamSlot + c * 6 + i] += v;
         }
       }
       double nv = 0.0;
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const double vn = tp[j] / ws.sinv_p[(size_t)g * 3 + j] - beta_old * ws.lv[(size_t)g * 3 + j];
+          const double old = beta_old != 0.0 ? ws.lv[(size_t)g * 3 + j] : 0.0;
+          const double vn = tp[j] / ws.sinv_p[(size_t)g * 3 + j] - beta_old * old;
           ws.lv[(size_t)g * 3 + j] = vn;
           nv += vn * vn;
         }
       }
       nv = warp_sum(nv);
-      if (lane == 0) my[n6] += nv;
+      if (lane == 0) my[0] += nv;
     }
-    reduce(n6 + 1);
-    if (threadIdx.x < n6) s_vc[threadIdx.x] = s_dc[threadIdx.x] * s_red[threadIdx.x] - beta_old * s_vc[threadIdx.x];
+    reduce(kCamSlot + n6);
+    if (threadIdx.x < n6) s_vc[threadIdx.x] = s_dc[threadIdx.x] * s_red[kCamSlot + threadIdx.x] - beta_old * s_vc[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-      double a2 = s_red[n6];
+      double a2 = s_red[0];
       for (int i = 0; i < n6; ++i) a2 += s_vc[i] * s_vc[i];
       S.alpha = sqrt(a2);
     }
@@ -1079,18 +1113,20 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
   };
 
   // ---- v = A^T u / alpha ; h = v ; hbar = 0 ; x = 0
-  for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) ws.lv[i] = 0.0;
-  __syncthreads();
+  // (every point vector is only ever touched by the thread that owns the point -- same g -> thread mapping in every
+  // pass -- so the only data that crosses threads are the reduction partials)
   pass_atu(0.0);
   {
     const double ia = S.alpha > 0.0 ? 1.0 / S.alpha : 0.0;
-    for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) {
-      const double v = ws.lv[i] * ia;
-      ws.lv[i] = v;
-      ws.lh[i] = v;
-      ws.lhb[i] = 0.0;
-      ws.gnp[i] = 0.0;
-    }
+    for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += stride)
+      for (int j = 0; j < 3; ++j) {
+        const size_t i = (size_t)g * 3 + j;
+        const double v = ws.lv[i] * ia;
+        ws.lv[i] = v;
+        ws.lh[i] = v;
+        ws.lhb[i] = 0.0;
+        ws.gnp[i] = 0.0;
+      }
     if (threadIdx.x < n6) {
       s_hc[threadIdx.x] = s_vc[threadIdx.x];
       s_hbc[threadIdx.x] = 0.0;
@@ -1119,16 +1155,40 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
   __syncthreads();
   const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
 
-  while (S.istop == 0 && S.itn < maxiter) {
-    // ---- u = A v - alpha u ; beta = |u|
+  // Each iteration is TWO passes over the points: the vector updates of iteration k (h, hbar, x need this
+  // iteration's rotations) ride in front of the "u = A v - alpha u" pass of iteration k + 1, whose reduction then
+  // carries |x_k| as well, and iteration k's stopping rules are evaluated there.  When they fire, x is final (the u
+  // that was just overwritten is not used again).
+  bool pending = false;    // iteration S.itn's vector updates and stopping test are outstanding
+  bool v_scaled = true;    // ws.lv holds v / alpha already
+  while (S.istop == 0) {
     {
       const double alpha = S.alpha, ib = S.inv_beta;
-      double acc = 0.0;
+      const double chb = S.c_hbar, cx = S.c_x, ch = S.c_h;
+      const double ia = (!v_scaled && S.alpha > 0.0) ? 1.0 / S.alpha : 1.0;
+      double acc = 0.0, accx = 0.0;
       for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += stride) {
         const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
         double vp[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) vp[j] = ws.lv[(size_t)g * 3 + j] / ws.sinv_p[(size_t)g * 3 + j];
+        for (int j = 0; j < 3; ++j) {
+          const size_t i = (size_t)g * 3 + j;
+          double v = ws.lv[i];
+          if (!v_scaled) {
+            v *= ia;
+            ws.lv[i] = v;
+          }
+          if (pending) {  // hbar = h + c_hbar hbar ; x += c_x hbar ; h = v + c_h h
+            const double h = ws.lh[i];
+            const double hb = ws.lhb[i] * chb + h;
+            const double x = ws.gnp[i] + cx * hb;
+            ws.lhb[i] = hb;
+            ws.gnp[i] = x;
+            ws.lh[i] = h * ch + v;
+            accx += x * x;
+          }
+          vp[j] = v / ws.sinv_p[i];
+        }
         for (int c = 0; c < C; ++c) {
           const double2 xy = __ldg(pts_xy + (size_t)c * TJ + g);
           if (xy.x == 0.0 || xy.y == 0.0) continue;
@@ -1147,17 +1207,55 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
         }
       }
       acc = warp_sum(acc);
-      if (lane == 0) my[n6] += acc;
+      accx = warp_sum(accx);
+      if (lane == 0) {
+        my[0] += acc;
+        my[1] += accx;
+      }
+      __syncthreads();  // every thread has read s_vc / the coefficients before the camera parts move on
+      if (pending && threadIdx.x < n6) {
+        const int i = threadIdx.x;
+        const double hb = s_hbc[i] * chb + s_hc[i];
+        s_hbc[i] = hb;
+        s_xc[i] += cx * hb;
+        s_hc[i] = s_hc[i] * ch + s_vc[i];
+      }
     }
-    reduce(n6 + 1);
+    reduce(2);
     if (threadIdx.x == 0) {
-      S.beta = sqrt(s_red[n6]);
-      S.inv_beta = S.beta > 0.0 ? 1.0 / S.beta : 0.0;
+      if (pending) {  // iteration S.itn's stopping rules
+        double x2 = s_red[1];
+        for (int i = 0; i < n6; ++i) x2 += s_xc[i] * s_xc[i];
+        S.normx = sqrt(x2);
+        const double test1 = S.normr / S.normb;
+        const double test2 = (S.normA * S.normr) != 0.0 ? S.normar / (S.normA * S.normr) : INFINITY;
+        const double test3 = 1.0 / S.condA;
+        const double t1 = test1 / (1.0 + S.normA * S.normx / S.normb);
+        const double rtol = btol + atol * S.normA * S.normx / S.normb;
+        int istop = 0;
+        if (S.itn >= maxiter) istop = 7;
+        if (1.0 + test3 <= 1.0) istop = 6;
+        if (1.0 + test2 <= 1.0) istop = 5;
+        if (1.0 + t1 <= 1.0) istop = 4;
+        if (test3 <= ctol) istop = 3;
+        if (test2 <= atol) istop = 2;
+        if (test1 <= rtol) istop = 1;
+        S.istop = istop;
+      }
+      if (S.istop == 0) {
+        S.beta = sqrt(s_red[0]);
+        S.inv_beta = S.beta > 0.0 ? 1.0 / S.beta : 0.0;
+      }
     }
     __syncthreads();
+    if (S.istop != 0) break;
+    v_scaled = true;
     // ---- v = A^T u - beta v ; alpha = |v|
-    if (S.beta > 0.0) pass_atu(S.beta);
-    // ---- rotations and estimates (every block, identical inputs)
+    if (S.beta > 0.0) {
+      pass_atu(S.beta);
+      v_scaled = false;
+    }
+    // ---- rotations and estimates of this iteration (every block, identical inputs)
     if (threadIdx.x == 0) {
       S.itn += 1;
       const double alpha = S.alpha, beta = S.beta;
@@ -1204,53 +1302,7 @@ ba_lsmr_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
       S.normar = fabs(S.zetabar);
     }
     __syncthreads();
-    // ---- hbar = h + c_hbar hbar ; x += c_x hbar ; h = v + c_h h ; |x|
-    {
-      const double chb = S.c_hbar, cx = S.c_x, ch = S.c_h;
-      const double ia = (S.beta > 0.0 && S.alpha > 0.0) ? 1.0 / S.alpha : 1.0;
-      double acc = 0.0;
-      for (int i = blockIdx.x * kBAThreads + threadIdx.x; i < TJ * 3; i += stride) {
-        const double v = S.beta > 0.0 ? ws.lv[i] * ia : ws.lv[i];
-        if (S.beta > 0.0) ws.lv[i] = v;
-        const double h = ws.lh[i];
-        const double hb = ws.lhb[i] * chb + h;
-        const double x = ws.gnp[i] + cx * hb;
-        ws.lhb[i] = hb;
-        ws.gnp[i] = x;
-        ws.lh[i] = h * ch + v;
-        acc += x * x;
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) my[n6] += acc;
-      if (threadIdx.x < n6) {
-        const int i = threadIdx.x;
-        const double hb = s_hbc[i] * chb + s_hc[i];
-        s_hbc[i] = hb;
-        s_xc[i] += cx * hb;
-        s_hc[i] = s_hc[i] * ch + s_vc[i];
-      }
-    }
-    reduce(n6 + 1);
-    if (threadIdx.x == 0) {
-      double x2 = s_red[n6];
-      for (int i = 0; i < n6; ++i) x2 += s_xc[i] * s_xc[i];
-      S.normx = sqrt(x2);
-      const double test1 = S.normr / S.normb;
-      const double test2 = (S.normA * S.normr) != 0.0 ? S.normar / (S.normA * S.normr) : INFINITY;
-      const double test3 = 1.0 / S.condA;
-      const double t1 = test1 / (1.0 + S.normA * S.normx / S.normb);
-      const double rtol = btol + atol * S.normA * S.normx / S.normb;
-      int istop = 0;
-      if (S.itn >= maxiter) istop = 7;
-      if (1.0 + test3 <= 1.0) istop = 6;
-      if (1.0 + test2 <= 1.0) istop = 5;
-      if (1.0 + t1 <= 1.0) istop = 4;
-      if (test3 <= ctol) istop = 3;
-      if (test2 <= atol) istop = 2;
-      if (test1 <= rtol) istop = 1;
-      S.istop = istop;
-    }
-    __syncthreads();
+    pending = true;
   }
   // ---- result: camera part of gn_h (point part is ws.gnp already)
   if (blockIdx.x == 0) {

@@ -187,8 +187,8 @@ def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e
     return rep
 
 
-def bundle_adjust_launches(max_iters):
-    opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8, 1)
+def bundle_adjust_launches(max_iters, solver="lsmr"):
+    opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8, 1 if solver == "lsmr" else 0)
     return int(lib.df3d_bundle_adjust_launches(C.byref(opts)))
 
 

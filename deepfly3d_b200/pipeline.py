@@ -40,7 +40,7 @@ def reorder_calib(calib, camera_ordering):
 
 class Pose3DPipeline:
     def __init__(self, state_dict, in_h, in_w, max_images, image_shape, camera_ordering=range(7), calib=None,
-                 device="cuda", mean=0.5, ba_max_iters=10, ba_ftol=1e-4, ba_max_frames=None):
+                 device="cuda", mean=0.5, ba_max_iters=10, ba_ftol=1e-4, ba_max_frames=None, ba_solver="lsmr"):
         self.device = torch.device(device)
         self.engine = HourglassEngine(state_dict, in_h, in_w, max_images, device=device, mean=mean)
         self.order = [int(c) for c in camera_ordering]
@@ -50,7 +50,7 @@ class Pose3DPipeline:
         cam_rt = np.stack([np.concatenate([rodrigues_vec(calib["R"][c]), calib["tvec"][c]]) for c in range(NUM_CAMERAS)])
         self.cam_rt0 = torch.as_tensor(cam_rt, device=self.device)
         self.intr4 = torch.as_tensor(intr_to_vec4(calib["intr"]), device=self.device)
-        self.ba_max_iters, self.ba_ftol, self.ba_max_frames = ba_max_iters, ba_ftol, ba_max_frames
+        self.ba_max_iters, self.ba_ftol, self.ba_max_frames, self.ba_solver = ba_max_iters, ba_ftol, ba_max_frames, ba_solver
         self._flip_cache = {}
         self._ba_ws = {}
 
@@ -102,7 +102,7 @@ class Pose3DPipeline:
         if key not in self._ba_ws:
             self._ba_ws[key] = ops.ba_workspace(*key, self.device)
         rep = ops.bundle_adjust(cam, self.intr4, ba_xy, X, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
-                                workspace=self._ba_ws[key])
+                                workspace=self._ba_ws[key], solver=self.ba_solver)
         P1, R1 = ops.projection_matrices(cam, self.intr4)
         X1 = ops.triangulate_dlt(P1, pxy)                        # own frames only
         return cam, R1, X1, rep
@@ -116,7 +116,7 @@ class Pose3DPipeline:
     def launches(self, n_images):
         """Kernel launches of one `run` (for bench.py's gpu_launches): hourglass plan + pack + 2 x
         (projection + DLT) + bundle adjustment."""
-        return self.engine.launches(n_images) + 1 + 4 + ops.bundle_adjust_launches(self.ba_max_iters)
+        return self.engine.launches(n_images) + 1 + 4 + ops.bundle_adjust_launches(self.ba_max_iters, self.ba_solver)
 
 
 def gather_frames(x, group=None, dim=0):
