@@ -296,7 +296,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def core_from_files(dev, frames=256):
+def core_from_files(dev, frames=256, ba_solver="exact"):
     """The drop-in surface end to end: writes `frames` x 7 synthetic 480x960 JPEG files, then times
     Core(folder) -> pose2d_estimation -> calibrate_calc -> save (threaded libjpeg decode, copy stream, device resize to
     256x512, 8-stack hourglass, BA, DLT, procrustes, pickle)."""
@@ -323,7 +323,11 @@ def core_from_files(dev, frames=256):
             list(pool.map(write, range(CAMS * frames)))
         sd = inference.random_state_dict(NUM_STACKS, seed=0)
         out = {}
-        for label, gpu_decode in (("host_libjpeg", False), ("nvjpeg", True)):
+        variants = [("host_libjpeg", False, None), ("nvjpeg", True, None), ("nvjpeg_gpu_hybrid", "gpu_hybrid", None)]
+        if os.environ.get("DF3D_BENCH_BLOCKS"):                          # tuning: extra block sizes, host decode
+            variants += [(f"host_libjpeg_block{b}", False, int(b)) for b in os.environ["DF3D_BENCH_BLOCKS"].split(",")]
+            variants += [(f"nvjpeg_block{b}", True, int(b)) for b in os.environ["DF3D_BENCH_BLOCKS"].split(",")]
+        for label, gpu_decode, block in variants:
             try:
                 times = []
                 for rep in range(2):                                    # first pass builds the engine (untimed)
@@ -332,7 +336,8 @@ def core_from_files(dev, frames=256):
                             shutil.rmtree(os.path.join(tmp, f))
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    core = Core(folder, num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6], state_dict=sd, gpu_decode=gpu_decode)
+                    core = Core(folder, num_images_max=0, camera_ordering=[0, 1, 2, 3, 4, 5, 6], state_dict=sd, gpu_decode=gpu_decode, block_frames=block,
+                                ba_solver=ba_solver)
                     t1 = time.perf_counter()
                     core.pose2d_estimation()
                     t2 = time.perf_counter()
@@ -344,13 +349,13 @@ def core_from_files(dev, frames=256):
                 tot, t_open, t_2d, t_3d, st = times[-1]
                 out[label] = {"frames_per_s": frames / tot, "pose2d_frames_per_s": frames / t_2d, "open_s": t_open, "pose2d_s": t_2d,
                               "calibrate_save_s": t_3d, "decode_wait_s": st.get("decode_wait_s"), "workers": st.get("workers"),
-                              "blocks": st.get("blocks")}
+                              "blocks": st.get("blocks"), "block_frames": st.get("block_frames"), "decode": st.get("decode")}
             except Exception as e:  # nvJPEG may be absent on a box: report, do not fail the bench
                 out[label] = {"error": str(e)[:200]}
         inference.drop_engine()
         return {"value": out.get("host_libjpeg", {}).get("frames_per_s"), "unit": "frames/s", "frames": frames,
                 "input": "7 x frames JPEG files 480x960 (quality 90) -> 256x512 network input, 8-stack hourglass, 64x128 heat-maps",
-                "path": "Core(folder).pose2d_estimation() + calibrate_calc() + save()", "variants": out}
+                "path": "Core(folder).pose2d_estimation() + calibrate_calc() + save()", "ba_solver": ba_solver, "variants": out}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -549,7 +554,7 @@ def run_b200(args):
                 import contextlib
 
                 with contextlib.redirect_stdout(sys.stderr):         # Core prints like the reference; stdout carries ONE line
-                    line["e2e_files"] = core_from_files(dev)
+                    line["e2e_files"] = core_from_files(dev, ba_solver=args.ba_solver)
             except Exception as e:
                 line["e2e_files"] = {"value": None, "error": str(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:

@@ -38,6 +38,8 @@ SIGNATURES = {
     "df3d_heatmap_argmax_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "df3d_resize_gray_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "df3d_jpeg_create": (_i, [C.POINTER(_vp)]),
+    "df3d_jpeg_create_backend": (_i, [C.POINTER(_vp), _i]),
+    "df3d_jpeg_backend": (_i, [_vp]),
     "df3d_jpeg_destroy": (None, [_vp]),
     "df3d_jpeg_info": (_i, [_vp, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "df3d_jpeg_decode_gray": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),

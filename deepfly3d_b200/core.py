@@ -74,10 +74,12 @@ class Core:
 
     def __init__(self, input_folder: str, output_folder: Optional[str] = None, num_images_max: Optional[int] = None,
                  camera_ordering: List[int] = [0, 1, 2, 3, 4, 5, 6], state_dict=None, weights=None, mean=None,
-                 gpu_decode=False, stream_videos=False):
+                 gpu_decode=False, stream_videos=False, block_frames=None, ba_solver="lsmr"):
         """Same four arguments as the reference.  Extra keywords (the reference reads them from its config,
         df3d/config.py:30-39): `weights` = hourglass checkpoint (sh8_deepfly.tar layout) or `state_dict`,
-        `mean` = per-channel mean or the path of a mean.pth.tar, `gpu_decode` = nvJPEG instead of libjpeg,
+        `mean` = per-channel mean or the path of a mean.pth.tar, `gpu_decode` = nvJPEG instead of libjpeg (True: hardware JPEG engines if present; "hardware" / "default"),
+        `block_frames` = frames per streamed block (default: sized for the GPU), `ba_solver` = "lsmr" (SciPy's own
+        truncated step, the default) or "exact" (see CameraNetwork.bundle_adjust),
         `stream_videos` = decode camera_N.mp4 straight into the pipeline instead of expanding them to JPEG files
         first (opt-in: the reference's frames have been through ffmpeg's MJPEG encoder once more)."""
         self.input_folder = input_folder
@@ -110,6 +112,7 @@ class Core:
         self.image_shape = shape                       # [W, H], e.g. [960, 480]
         self.camera_ordering = self.setup_camera_ordering(camera_ordering)
         self._state_dict, self._weights, self._mean, self._gpu_decode = state_dict, weights, mean, gpu_decode
+        self._block_frames, self._ba_solver = block_frames, ba_solver
         self.ingest_stats = {}
 
         self.camNet = None
@@ -179,6 +182,7 @@ class Core:
             folder=self.input_folder, camera_ids_to_flip=flip, return_heatmap=False, return_confidence=True,
             max_img_id=self.max_img_id, batch_size=batch_size, disable_pin_memory=disable_pin_memory,
             state_dict=self._state_dict, weights=self._weights, mean=self._mean, gpu_decode=self._gpu_decode,
+            block_frames=self._block_frames,
             stats=self.ingest_stats, source="videos" if self._stream_videos else "images")
         self.conf = conf
         # packing runs on the device from the integer arg-max indices (bit-exact with core.py:187-203)
@@ -202,7 +206,7 @@ class Core:
         }
         image_path = os.path.join(self.input_folder, "camera_{cam_id}_img_{img_id}.jpg")
         self.camNet = CameraNetwork(self.points2d * self.image_shape[::-1], calib=calib_reordered, image_path=image_path)
-        self.camNet.bundle_adjust(update_intrinsic=False, update_distort=False)
+        self.camNet.bundle_adjust(update_intrinsic=False, update_distort=False, solver=self._ba_solver)
         print(f"Reprojection error is {self.camNet.reprojection_error()}")
 
     def get_points3d(self):

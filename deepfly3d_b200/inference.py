@@ -298,12 +298,12 @@ def drop_engine():
 _JPEG = {}
 
 
-def _jpeg_decoder():
+def _jpeg_decoder(backend=None):
     from . import ops
 
-    dec = _JPEG.get("dec")
+    dec = _JPEG.get(backend)
     if dec is None:
-        dec = _JPEG["dec"] = ops.JpegDecoder()
+        dec = _JPEG[backend] = ops.JpegDecoder(backend)
     return dec
 
 
@@ -326,6 +326,10 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
     bf = int(block_frames) if block_frames else block_frames_for(in_h, in_w, T, batch_size)
+    if not block_frames and not gpu_decode and bf >= 16:
+        # host decode is the slower side of the stream: half-size blocks start the GPU earlier (the first block is
+        # the only one whose decode nothing hides) and still fill it (measured: 698 -> 876 frames/s on 256 frames)
+        bf //= 2
     blocks = plan_blocks(T, bf)
     dev = torch.device(device)
     eng = get_engine(state_dict, in_h, in_w, NUM_CAMERAS * bf, device=device, mean=load_mean(mean), weights=weights)
@@ -346,7 +350,24 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
         main = torch.cuda.current_stream()
         copy_stream = torch.cuda.Stream()
         if gpu_decode:
-            pending = rd.read_bytes_async(*blocks[0])
+            # device-side decode: the files are read by the pool, the block is decoded on a side stream (hardware
+            # JPEG engines where the GPU has them) while the hourglass of the previous block runs on the main one
+            dec = _jpeg_decoder(gpu_decode if isinstance(gpu_decode, str) else None)
+            dec_stream = torch.cuda.Stream()
+
+            def submit_decode(futures):
+                nonlocal wait_s
+                t_w = time.perf_counter()
+                data = rd.wait(futures)
+                wait_s += time.perf_counter() - t_w
+                with torch.cuda.stream(dec_stream):
+                    frames = dec.decode_gray(data, device=dev)    # (7*tc, Hs, Ws), camera-major
+                    ev = torch.cuda.Event()
+                    ev.record(dec_stream)
+                return frames, ev, data
+
+            decoded = submit_decode(rd.read_bytes_async(*blocks[0]))
+            pending = rd.read_bytes_async(*blocks[1]) if len(blocks) > 1 else None
         else:
             Hs, Ws = rd.shape
             host = [torch.empty((NUM_CAMERAS, bf, Hs, Ws), dtype=torch.uint8) for _ in range(2)]
@@ -361,14 +382,14 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
         for k, (t0, t1) in enumerate(blocks):
             tc = t1 - t0
             slot = k & 1
-            t_w = time.perf_counter()
-            got = rd.wait(pending)                               # block k decoded (or its bytes read)
-            wait_s += time.perf_counter() - t_w
             if gpu_decode:
-                if k + 1 < len(blocks):
-                    pending = rd.read_bytes_async(*blocks[k + 1])
-                native = _jpeg_decoder().decode_gray(got, device=dev)          # (7*tc, Hs, Ws), camera-major
+                native, ev, keep = decoded
+                main.wait_event(ev)
+                native.record_stream(main)
             else:
+                t_w = time.perf_counter()
+                rd.wait(pending)                                 # block k decoded
+                wait_s += time.perf_counter() - t_w
                 if k + 1 < len(blocks):
                     if k >= 1:
                         uploaded[slot ^ 1].synchronize()         # the other host buffer has left for the device
@@ -387,12 +408,19 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
             conf_all[:, t0:t1] = res[1].view(NUM_CAMERAS, tc, K)
             if not gpu_decode:
                 consumed[slot].record(main)
+            else:
+                if pending is not None:                          # decode of block k+1 overlaps the forward of block k
+                    decoded = submit_decode(pending)
+                    pending = rd.read_bytes_async(*blocks[k + 2]) if k + 2 < len(blocks) else None
+                ev.synchronize()                                 # block k is decoded (it ran ahead of its forward):
+                keep = None                                      # its compressed streams may go
             if return_heatmap:
                 heat_all[:, t0:t1] = res[2][..., :K].permute(0, 3, 1, 2).reshape(NUM_CAMERAS, tc, K, hh, hw).cpu()
         idx_h = idx_all.cpu().numpy().astype(np.int64)
         conf_h = conf_all.cpu().numpy()
     if stats is not None:
-        stats.update(blocks=len(blocks), block_frames=bf, decode_wait_s=wait_s, workers=rd.workers)
+        stats.update(blocks=len(blocks), block_frames=bf, decode_wait_s=wait_s, workers=rd.workers,
+                     decode=("nvjpeg-" + dec.backend) if gpu_decode else "host")
     points2d = np.stack([(idx_h // hw) / hh, (idx_h % hw) / hw], axis=-1).astype(np.float64)
     out = [points2d]
     if return_heatmap:

@@ -67,11 +67,18 @@ def resize_gray_u8(images, size_hw):
 
 class JpegDecoder:
     """Device-side JPEG decode (luminance) through nvJPEG, bound at run time.  Opt-in: a few grey levels away
-    from the host's libjpeg read, see include/df3d_b200.h."""
+    from the host's libjpeg read, see include/df3d_b200.h.  backend: None = the GPU's hardware JPEG engines when
+    the box has them, else nvJPEG's default; "hardware" / "default" ask for one (RuntimeError if absent)."""
 
-    def __init__(self):
+    BACKENDS = {None: -1, "hardware": 3, "gpu_hybrid": 2, "default": 0}
+
+    def __init__(self, backend=None):
         self._h = C.c_void_p()
-        check(lib.df3d_jpeg_create(C.byref(self._h)))
+        check(lib.df3d_jpeg_create_backend(C.byref(self._h), self.BACKENDS[backend]))
+
+    @property
+    def backend(self):
+        return {3: "hardware", 2: "gpu_hybrid", 0: "default"}[lib.df3d_jpeg_backend(self._h)]
 
     def close(self):
         if self._h:
@@ -87,19 +94,19 @@ class JpegDecoder:
     def image_size(self, data):
         """-> (H, W) of a compressed stream (bytes)."""
         w, h = C.c_int(), C.c_int()
-        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
-        check(lib.df3d_jpeg_info(self._h, buf, len(data), C.byref(w), C.byref(h)))
+        check(lib.df3d_jpeg_info(self._h, C.cast(C.c_char_p(data), C.c_void_p), len(data), C.byref(w), C.byref(h)))
         return h.value, w.value
 
     def decode_gray(self, streams, device="cuda"):
-        """streams: list of bytes, all of one size -> (n, H, W) uint8 tensor on the device."""
+        """streams: list of bytes, all of one size -> (n, H, W) uint8 tensor on the device (work enqueued on the
+        current stream; keep `streams` alive until it has run)."""
         n = len(streams)
         if n == 0:
             return torch.empty((0, 0, 0), dtype=torch.uint8, device=device)
+        streams = [bytes(s) for s in streams]                      # no copy for bytes objects
         H, W = self.image_size(streams[0])
         out = torch.empty((n, H, W), dtype=torch.uint8, device=device)
-        bufs = [(C.c_ubyte * len(s)).from_buffer_copy(s) for s in streams]
-        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(s), C.c_void_p).value for s in streams])   # the bytes' own buffers
         lens = (C.c_size_t * n)(*[len(s) for s in streams])
         with torch.cuda.device(out.device):
             check(lib.df3d_jpeg_decode_gray(self._h, ptrs, lens, n, _ptr(out), H, W, _stream()))

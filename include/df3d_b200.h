@@ -78,9 +78,16 @@ int df3d_resize_gray_u8(const uint8_t* src_dev, int B, int Hs, int Ws, uint8_t* 
  * DCT differs from libjpeg's by a few grey levels, so results are NOT bit-identical to the host read.
  *
  *   data, lens : HOST arrays of n compressed streams        dst_dev : (n, H, W) uint8 on the device
+ *
+ * df3d_jpeg_create probes the GPU's hardware JPEG engines first (nvJPEG backend 3, the frame block decoded with
+ * nvjpegDecodeBatched) and settles for nvJPEG's default backend (0: one nvjpegDecode per image, Huffman stage on
+ * the calling host thread) where the device or driver exposes none; df3d_jpeg_create_backend asks for one of
+ * those or for backend 2 (GPU-hybrid: batched, Huffman stage on the SMs; DF3D_EUNSUPPORTED if it is not there); df3d_jpeg_backend reports the backend in use.
  * ------------------------------------------------------------------------------------------ */
 typedef struct df3d_jpeg df3d_jpeg;
 int df3d_jpeg_create(df3d_jpeg** out);
+int df3d_jpeg_create_backend(df3d_jpeg** out, int backend);
+int df3d_jpeg_backend(const df3d_jpeg* j);
 void df3d_jpeg_destroy(df3d_jpeg* j);
 int df3d_jpeg_info(df3d_jpeg* j, const uint8_t* data, size_t len, int* width, int* height);
 int df3d_jpeg_decode_gray(df3d_jpeg* j, const uint8_t* const* data, const size_t* lens, int n, uint8_t* dst_dev,

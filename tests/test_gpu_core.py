@@ -174,6 +174,32 @@ def test_inference_folder_streams_blocks_and_loads_checkpoint(working, tmp_path)
     inference.drop_engine()
 
 
+def test_inference_folder_device_decode_streams_blocks(working):
+    """gpu_decode: files read by the pool, blocks decoded with nvJPEG on a side stream (hardware engines when the box has
+    them) overlapping the previous block's hourglass.  Same result whatever the block size; against the host-decode
+    path the decoded frames differ by a grey level or two (tests/test_gpu_ingest.py), so the heat-map scores agree
+    closely and most arg-maxes exactly."""
+    from deepfly3d_b200 import inference
+
+    sd = ohg.make_model(2, seed=0).state_dict()
+    kw = dict(folder=working, camera_ids_to_flip=[4, 5, 6], max_img_id=2, state_dict=sd)
+    p_h, c_h = inference.inference_folder(**kw)
+    stats = {}
+    p_1, c_1 = inference.inference_folder(gpu_decode=True, stats=stats, **kw)
+    assert stats["blocks"] == 1 and stats["decode"] in ("nvjpeg-hardware", "nvjpeg-default")
+    print(f"  device decode backend: {stats['decode']}")
+    p_3, c_3 = inference.inference_folder(gpu_decode=True, block_frames=1, stats=stats, **kw)        # three blocks
+    assert stats["blocks"] == 3
+    assert np.array_equal(p_1, p_3) and np.array_equal(c_1, c_3)
+    p_d, c_d = inference.inference_folder(gpu_decode="default", block_frames=2, **kw)
+    if stats["decode"] == "nvjpeg-default":
+        assert np.array_equal(p_1, p_d) and np.array_equal(c_1, c_d)
+    for p, c in ((p_1, c_1), (p_d, c_d)):
+        assert np.abs(c - c_h).max() < 0.02 * max(float(np.abs(c_h).max()), 1e-6) + 1e-3
+        assert (np.abs(p - p_h).max(axis=-1) <= 0.02).mean() > 0.8
+    inference.drop_engine()
+
+
 def _sharded_worker(rank, world, port, T, out_dir):
     import torch.distributed as dist
 
