@@ -69,7 +69,7 @@ enum { kEpiReluX = 0, kEpiReluOut, kEpiResOutAct, kEpiResUpOutAct, kEpiResOut, k
 struct StageLite {
   unsigned long long out;  // bf16 output base or 0
   unsigned long long pool_raw, pool_act;  // pooled outputs or 0
-  int n, kblocks, has_res, x_src, kind, col[2][2], aff_off, unit, hz, hzd, pool_off, ssk, pad;
+  int n, kblocks, has_res, x_src, kind, col[2][2], aff_off, unit, hz, hzd, pool_off, ssk, stg;
 };
 static_assert(sizeof(StageLite) == 88, "StageLite layout");
 constexpr int kLiteStride = 96;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       prefetch_tensormap(&p.st[i].tmB);
       if (p.st[i].has_res) prefetch_tensormap(&p.st[i].tmRes);
       if (p.st[i].has_res2) prefetch_tensormap(&p.st[i].tmRes2);
-      if (p.st[i].has_res && p.st[i].out_raw) prefetch_tensormap(&p.st[i].tmOutQ);
+      if ((p.st[i].has_res || p.st[i].stage_out) && p.st[i].out_raw) prefetch_tensormap(&p.st[i].tmOutQ);
       if (p.st[i].ss_kblocks) prefetch_tensormap(&p.st[i].tmA2);
     }
     for (int s = 0; s < p.n_m; ++s) {
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     l->pool_raw = reinterpret_cast<unsigned long long>(st.pool_raw);
     l->pool_act = reinterpret_cast<unsigned long long>(st.pool_act);
     l->pool_off = st.pool_off;
+    l->stg = st.stage_out;
   }
   // per-channel epilogue constants of every stage -> shared memory, only the arrays the stage uses:
   // [scale1 n (unless it is 1)][shift1 n][scale2 n][shift2 n (when the operand is relu(bn2(.)))]
@@ -340,14 +341,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         decode_tile(2 * pt + (int)rank, x0, y0, n0);
         for (int i = 0; i < n_chain; ++i) {
           const ChainStage& st = p.st[i];
-          if (!st.has_res) continue;
+          if (!st.has_res && !st.stage_out) continue;
           const int nsl = st.n >> 6;
           for (int sl = 0; sl < nsl; ++sl) {
             mbar_wait(sempty(u), ph ^ 1u);
             const uint32_t slab = s_base + u * (uint32_t)p.slab_bytes;
-            mbar_arrive_expect_tx(sfull(u), kUnitBytes + (st.has_res2 ? kUnitBytes / 4 : 0));
-            tma_load_4d(slab, &st.tmRes, sfull(u), sl * 64, x0, y0, n0);
-            if (st.has_res2) tma_load_4d(slab + kUnitBytes, &st.tmRes2, sfull(u), sl * 64, x0 >> 1, y0 >> 1, n0);
+            if (st.stage_out) {  // blank slab: the epilogue stages its output in it
+              mbar_arrive(sfull(u));
+            } else {
+              mbar_arrive_expect_tx(sfull(u), kUnitBytes + (st.has_res2 ? kUnitBytes / 4 : 0));
+              tma_load_4d(slab, &st.tmRes, sfull(u), sl * 64, x0, y0, n0);
+              if (st.has_res2) tma_load_4d(slab + kUnitBytes, &st.tmRes2, sfull(u), sl * 64, x0 >> 1, y0 >> 1, n0);
+            }
             if (++u == (uint32_t)p.n_slabs) {
               u = 0;
               ph ^= 1u;
@@ -607,6 +612,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     auto run_stage = [&](int i, int t, int x0, int y0, int n0, const TilePix& tp) {
       const StageLite& st = lite(i);
       const bool has_res = st.has_res != 0;
+      const bool has_slab = has_res || st.stg != 0;  // works on a slab of the ring (residual, or blank for a staged output)
       const int x_src = st.x_src, kind = st.kind;
       const int nsl = st.n >> 6;
       uint8_t* out_row[2];
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       for (int sl = grp; sl < nsl; sl += 2) {
         uint32_t su = 0, slab = s_base;
         const uint32_t t_slab = ((sl >> 1) ? t_hi : t_lo) + (sl & 1) * 64;
-        if (has_res) {
+        if (has_slab) {
           su = spos + (uint32_t)sl;
           uint32_t sph = sphase;
           while (su >= n_slabs) {
@@ -666,8 +672,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             else    epi_slab<true, true, false, false, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiResOut
           }
         } else {
-          if (x_src) epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluX
-          else       epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiReluOut
+          if (x_src)       epi_slab<false, false, false, true, 1, false>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluX
+          else if (has_slab) epi_slab<false, false, false, true, 0, true, false, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluOut, staged
+          else             epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiReluOut
         }
         if (x_src) {  // this slab = one K block of the next stage's operand: hand it to the MMA warp first (the stores
                       // and the pooling below are off the chain's critical path)
@@ -676,7 +683,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(epislab_l(i, sl));
         }
-        if (has_res && st.out) {
+        if (has_slab && st.out) {
           // in-place output: this warp's 32 rows of the slab go out as one TMA store; the slab is handed back
           // to the producer once the store has read it -- one slab later, so that nobody waits for that
           fence_proxy_async();
@@ -738,12 +745,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             }
             pending = su;
           }
-        } else if (has_res) {  // slab consumed by this warp
+        } else if (has_slab) {  // slab consumed by this warp
           __syncwarp();
           if (lane == 0) mbar_arrive(sempty(su));
         }
       }
-      if (has_res) {
+      if (has_slab) {
         spos += (uint32_t)nsl;
         while (spos >= n_slabs) {
           spos -= n_slabs;
@@ -946,7 +953,9 @@ int launch_conv_chain(const ChainParams& p_in, int num_sms, cudaStream_t stream)
       st.pool_off = aff_floats;
       aff_floats += 2 * st.n;
     }
-    any_slab |= st.has_res != 0;
+    // stored stages without a residual leave through a blank slab + TMA store when the caller provided the store map
+    st.stage_out = (st.epi_kind == kEpiReluOut && p.tw * p.th * p.nb == 128 && !getenv("DF3D_CHAIN_NO_STAGE_OUT")) ? 1 : 0;
+    any_slab |= st.has_res != 0 || st.stage_out != 0;
     any_res2 |= st.has_res2 != 0;
   }
   if (int e = plan_tmem(p)) return e;

@@ -22,7 +22,7 @@ struct ChainStage {
   CUtensorMap tmB;     // weights, 2-D (K, N) K-major, box (64, 64) = one CTA's half of a 128-row block, SWIZZLE_128B
   CUtensorMap tmRes;   // residual added in this stage's epilogue: 4-D box (64, tw, th, nb)
   CUtensorMap tmRes2;  // second residual at half resolution (nearest x2 up-sample + add)
-  CUtensorMap tmOutQ;  // stages with a residual AND out_raw: out_raw as a TMA store target, box = one warp's quarter of
+  CUtensorMap tmOutQ;  // stages with out_raw: out_raw as a TMA store target, box = one warp's quarter of
                        // the tile (64 channels x 32 consecutive pixels, see make_tmap_quarter)
   // epilogue:  v = acc*scale1[c] + shift1[c] (+ residual) (+ up(residual2)) ; relu1 ;
   //            raw = bf16(v) ; act = bf16(relu(raw*scale2[c] + shift2[c]))
@@ -58,6 +58,11 @@ struct ChainStage {
                  // n = 128); plans whose column assignment alternates between consecutive tiles differ by parity
   int hz_stage;  // epilogue that must have drained those columns before this stage is issued (-1: implied)
   int hz_delta;  // ... of this tile (0) or of the previous one (1)
+  // filled by launch_conv_chain: a stored stage WITHOUT a residual writes its output into a blank slab of the
+  // residual ring and leaves through tmOutQ like the stages with one (needs tmOutQ).  256-bit stores from registers
+  // cost the L1 data pipe ~6x the wavefronts of the same bytes staged through shared memory, and that pipe (LSU +
+  // tensor-core operand reads) is what bounds the chains
+  int stage_out;
   int aff_off;   // float offset of this stage's constants in shared memory (filled by the launcher)
   int pool_off;  // ... of the pooled output's scale / shift (filled by the launcher)
   int epi_kind;  // specialised epilogue variant (filled by the launcher)

@@ -89,7 +89,8 @@ struct EpiRow {
 // c1/h1/c2/h2: the constant arrays at this lane's first channel.
 //   STAGED  conv_gemm.cu: bf16(v) and / or the activated value go to 128B-swizzled shared-memory staging tiles
 //           (TMA stores follow) instead of global memory / tensor memory
-template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT, bool STAGED = false>
+//   INPLACE the output goes into the slab row (rrow_s) although there is no residual in it (blank slab of the ring)
+template <bool UNIT, bool RES, bool RES2, bool RELU, int XSRC, bool OUT, bool STAGED = false, bool INPLACE = false>
 __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restrict__ sc1,
                                          const float4* __restrict__ sh1, const float4* __restrict__ sc2,
                                          const float4* __restrict__ sh2, const EpiRow (&row)[2], uint32_t x_addr,
@@ -167,7 +168,7 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
       }
       if (XSRC == 1) tmem_st_16x32bx2_x4(x_addr + ((uint32_t)(16 * w) << 16) + 4 * j, op);
       if (XSRC == 2) tmem_st_16x32bx2_x4(x_addr + ((uint32_t)(16 * w) << 16) + 4 * j, xp);
-      if (OUT && RES) {
+      if (OUT && (RES || INPLACE)) {
         // Stored stage with a residual: bf16(v) replaces the residual chunk it was computed from, in place in
         // the slab; the warp's 32 rows then leave with one TMA store (run_stage).  256-bit stores from
         // registers cost the LSU data pipe ~50 wavefronts per instruction (measured: 4 900 of 9 500 per tile).

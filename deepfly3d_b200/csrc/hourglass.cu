@@ -679,7 +679,7 @@ struct Emitter {
           return;
         }
         st.out_raw = reinterpret_cast<__nv_bfloat16*>(ptr(*s.out_raw));
-        if (st.has_res && (err = make_tmap_quarter(&st.tmOutQ, ptr(*s.out_raw), s.N, in.W, in.H, B, tw, th, nb))) return;
+        if (s.out_raw && (err = make_tmap_quarter(&st.tmOutQ, ptr(*s.out_raw), s.N, in.W, in.H, B, tw, th, nb))) return;
         bytes_px += 2.0 * s.N;
       }
       if (s.pool_raw && s.pool_raw->valid && s.pool_act && s.pool_act->valid) {

@@ -326,10 +326,11 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
     bf = int(block_frames) if block_frames else block_frames_for(in_h, in_w, T, batch_size)
-    if not block_frames and not gpu_decode and bf >= 16:
-        # host decode is the slower side of the stream: half-size blocks start the GPU earlier (the first block is
-        # the only one whose decode nothing hides) and still fill it (measured: 698 -> 876 frames/s on 256 frames)
-        bf //= 2
+    if not block_frames and not gpu_decode and bf >= 32:
+        # host decode is the slower side of the stream: quarter-size blocks start the GPU earlier (the first block is
+        # the only one whose decode nothing hides) and still fill it (measured on 256 frames of 480x960 JPEGs, 16 host
+        # cores: 128-frame blocks 698, 64-frame 808, 32-frame 949 frames/s through pose2d_estimation)
+        bf //= 4
     blocks = plan_blocks(T, bf)
     dev = torch.device(device)
     eng = get_engine(state_dict, in_h, in_w, NUM_CAMERAS * bf, device=device, mean=load_mean(mean), weights=weights)

@@ -126,6 +126,7 @@ int main(int argc, char** argv) {
     ChainStage& s2 = stage(256, 128, 9 * 128 * 128 + 256 * 128 + 2 * 256 * 256);
     s2.relu1 = 1;
     s2.out_raw = t1n;
+    rc |= make_tmap_quarter(&s2.tmOutQ, t1n, 128, W, H, B, tw, th, nb);
     names[n - 1] = "c1'";
   }
   p.n_chain = n;
