@@ -592,6 +592,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     unsigned long long* const dbg = (kProbe && blockIdx.x == 0 && lane == 0 && q == 0) ? p.dbg : nullptr;
     int di = 4096 * (1 + grp);
     const int dend = di + 4000;
+    // probe, dbg_exec & 4: five stamps per slab of group 0 in a fourth region (loop top, slab ready, math done, operand
+    // handed over, store issued)
+    unsigned long long* const dbs = (kProbe && dbg && grp == 0 && (p.dbg_exec & 4)) ? p.dbg + 3 * 4096 : nullptr;
+    int ds = 0;
+    auto stamp = [&]() {
+      if (kProbe && dbs && ds < 4000) dbs[ds++] = clock64();
+    };
 
     // epilogue of stage i of the tile (local number t) at pixel offsets x0, y0, n0
     // pixel index of this lane's two rows for a tile at (x0, y0, n0), and whether they lie inside the batch
@@ -632,6 +639,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 #pragma unroll 1
       for (int sl = grp; sl < nsl; sl += 2) {
         uint32_t su = 0, slab = s_base;
+        stamp();
         const uint32_t t_slab = ((sl >> 1) ? t_hi : t_lo) + (sl & 1) * 64;
         if (has_slab) {
           su = spos + (uint32_t)sl;
@@ -643,6 +651,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           mbar_wait_warp(sfull(su), sph);
           slab = s_base + su * slab_bytes_r;
         }
+        stamp();
         EpiRow row[2];
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
@@ -676,6 +685,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           else if (has_slab) epi_slab<false, false, false, true, 0, true, false, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);  // kEpiReluOut, staged
           else             epi_slab<false, false, false, true, 0, true>(t_slab, c1, h1, c2, h2, row, t_slab, h);   // kEpiReluOut
         }
+        stamp();
         if (x_src) {  // this slab = one K block of the next stage's operand: hand it to the MMA warp first (the stores
                       // and the pooling below are off the chain's critical path)
           tmem_st_wait();
@@ -683,6 +693,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(epislab_l(i, sl));
         }
+        stamp();
         if (has_slab && st.out) {
           // in-place output: this warp's 32 rows of the slab go out as one TMA store; the slab is handed back
           // to the producer once the store has read it -- one slab later, so that nobody waits for that
@@ -749,6 +760,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive(sempty(su));
         }
+        stamp();
       }
       if (has_slab) {
         spos += (uint32_t)nsl;

@@ -43,13 +43,13 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&half, px / 4 * 256 * 2));
   CK(cudaMalloc(&wts, (size_t)(9 * 128 * 128 + 4 * 256 * 256) * 2));
   CK(cudaMalloc(&aff, 4096 * 4));
-  CK(cudaMalloc(&dbg, 3 * 4096 * 8));
+  CK(cudaMalloc(&dbg, 4 * 4096 * 8));
   CK(cudaMemset(t1, 0, px * 128 * 2));
   CK(cudaMemset(res, 0, px * 256 * 2));
   CK(cudaMemset(half, 0, px / 4 * 256 * 2));
   CK(cudaMemset(wts, 0, (size_t)(9 * 128 * 128 + 4 * 256 * 256) * 2));
   CK(cudaMemset(aff, 0, 4096 * 4));
-  CK(cudaMemset(dbg, 0, 3 * 4096 * 8));
+  CK(cudaMemset(dbg, 0, 4 * 4096 * 8));
 
   ChainParams p;
   memset(&p, 0, sizeof(p));
@@ -150,7 +150,7 @@ int main(int argc, char** argv) {
     const int tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     printf("run %d: %.3f ms, %d tiles, %.2f us/tile/SM\n", it, ms, tiles, ms * 1e3 / ((tiles + 147) / 148));
   }
-  std::vector<unsigned long long> h(3 * 4096);
+  std::vector<unsigned long long> h(4 * 4096);
   CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
   // MMA warp stamps: head(0) start/issued, then per tile: for each stage i >= 1 (ready, issued), with the next
   // head's (start, issued) behind stage head_after.  Epilogue stamps: (ready, done) per stage in its own order.
@@ -174,6 +174,18 @@ int main(int argc, char** argv) {
         printf(" (%llu, %llu, %llu)", h[k] - h[k - 1], h[k + 1] - h[k], h[k + 2] - h[k + 1]);
       }
       printf("\n");
+    }
+  }
+  if (p.dbg_exec & 4) {
+    // group 0's slabs in program order: per tile (steady state) stage 1 has n1/128 slabs of this group, the head and the
+    // other stages n/128 each
+    int per_tile = 0;
+    for (int i = 0; i < n; ++i) per_tile += p.st[i].n >> 7;
+    printf("epilogue group 0, slabs of tiles 20..21 (%d slabs per tile): (wait for the slab, tcgen05.ld + math, operand hand-over, store) and the gap to the next slab\n", per_tile);
+    for (int sidx = 20 * per_tile; sidx < 22 * per_tile; ++sidx) {
+      const size_t k = 3 * 4096 + (size_t)sidx * 5;
+      printf("  slab %d: (%llu, %llu, %llu, %llu) gap %llu\n", sidx, h[k + 1] - h[k], h[k + 2] - h[k + 1], h[k + 3] - h[k + 2], h[k + 4] - h[k + 3],
+             h[k + 5] - h[k + 4]);
     }
   }
   return 0;

@@ -2,7 +2,7 @@
 # GPU session: full gpu test suite, smoke, bench, and (with "ncu") the ncu launch list of one bench
 # step + full captures of the dominant kernels.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-( timeout -s KILL 400 python -m pytest tests -q -m gpu --no-header -rA -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" ) | tee gpurun_out/summary.txt
+( timeout -s KILL 900 python -m pytest tests -q -m gpu --no-header -rA -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" ) | tee gpurun_out/summary.txt
 ( timeout -s KILL 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" ) | tee -a gpurun_out/summary.txt
 ( timeout -s KILL 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit=$?" ) | tee -a gpurun_out/summary.txt
 tail -3 gpurun_out/bench.log
@@ -19,7 +19,7 @@ if [ "$1" = "ncu" ]; then
       python bench.py --profile --frames 256 --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full conv exit=$?" | tee -a gpurun_out/summary.txt
   timeout -s KILL 400 ncu --nvtx --nvtx-include "df3d_step/" --set full --clock-control none --import-source on \
-      -k regex:'argmax|pack_points|triangulate|ba_gradient|ba_schur|ba_solve|ba_backsub|ba_step|proc_median|proc_apply' -c 16 -f -o gpurun_out/prof_tail \
+      -k regex:'argmax|pack_points|triangulate|ba_gradient|ba_schur|ba_solve|ba_lsmr|ba_backsub|ba_step|proc_median|proc_apply' -c 16 -f -o gpurun_out/prof_tail \
       python bench.py --profile --frames 256 --steps 1 --warmup 3 > gpurun_out/ncu_tail.log 2>&1
   echo "ncu full tail exit=$?" | tee -a gpurun_out/summary.txt
 fi
