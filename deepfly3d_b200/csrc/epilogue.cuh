@@ -50,6 +50,14 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 __device__ __forceinline__ float2 bf2_unpack(uint32_t x) { return make_float2(bf_lo(x), bf_hi(x)); }
+// bf16x2 + bf16x2 with ONE rounding (HADD2.BF16): bit-identical to unpacking both, adding in fp32 and packing again
+// -- the fp32 sum of two bf16 values is exact unless their exponents are more than 16 apart, and then neither
+// rounding moves the larger operand (checked on 8 M random pairs, tools/check_bf16_add.py) -- in 1 instruction for 6
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 
 // Operands of one group of 8 channels of a slab, fetched from shared memory two groups ahead of their use
 // (unused members are dead code in the specialisations that do not need them).
@@ -152,9 +160,12 @@ __device__ __forceinline__ void epi_slab(uint32_t t_slab, const float4* __restri
         const float2 ac = make_float2(__uint_as_float(a[2 * e]), __uint_as_float(a[2 * e + 1]));
         float2 v = UNIT ? fadd2(ac, t1[e]) : ffma2(ac, s1[e], t1[e]);
         if (RES) v = fadd2(v, bf2_unpack(rw[e]));
-        if (RES2)  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
-          v = fadd2(bf2_unpack(pack2(v.x, v.y)), bf2_unpack(uw[e]));
-        op[e] = RELU ? pack2_relu(v.x, v.y) : pack2(v.x, v.y);
+        if (RES2 && !RELU) {  // up1 + nearest_x2(low3): the sum is rounded to bf16 first, like a stored up1
+          op[e] = add_bf16x2(pack2(v.x, v.y), uw[e]);
+        } else {
+          if (RES2) v = fadd2(bf2_unpack(pack2(v.x, v.y)), bf2_unpack(uw[e]));
+          op[e] = RELU ? pack2_relu(v.x, v.y) : pack2(v.x, v.y);
+        }
         if (XSRC == 2) {  // act = relu(bn(bf16(v))): the rounded value is the packed one
           const float2 x = ffma2(bf2_unpack(op[e]), s2[e], t2[e]);
           xp[e] = pack2_relu(x.x, x.y);
