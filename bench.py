@@ -381,8 +381,13 @@ def run_b200(args):
 
     T, scaling = frames_for(args, world)
     n_img = CAMS * T
+    # configs[3]: BA on a strided subset of <= 1 000 frames; configs[2]: over all frames (DF3D_BENCH_BA_MAX_FRAMES only
+    # serves the multi-GPU attribution runs of tools/gpu_n8.sh and is named in the line when set)
+    ba_cap = 1000 if args.config == 4 else None
+    if os.environ.get("DF3D_BENCH_BA_MAX_FRAMES"):
+        ba_cap = int(os.environ["DF3D_BENCH_BA_MAX_FRAMES"])
     pipe = Pose3DPipeline(random_state_dict(NUM_STACKS, seed=0), IN_H, IN_W, n_img, image_shape=[IN_W, IN_H],
-                          device=dev, ba_max_iters=10, ba_max_frames=1000 if args.config == 4 else None, ba_solver=args.ba_solver)
+                          device=dev, ba_max_iters=10, ba_max_frames=ba_cap, ba_solver=args.ba_solver)
     images = synthetic_images(T, IN_H, IN_W, seed=1 + rank, device=dev)      # resident in HBM
     host_images = torch.empty((n_img, IN_H, IN_W), dtype=torch.uint8).pin_memory()
     host_images.copy_(images)
@@ -521,7 +526,9 @@ def run_b200(args):
         with open(prof) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     d2h = int(host_x3d.numel() * 8 * 2 + host_cam.numel() * 8) if full3d else int(host_idx.numel() * 4 + host_conf.numel() * 4)
-    launches = int(pipe.launches(n_img) + 4) if full3d else int(pipe.engine.launches(n_img))
+    ba_frames = next(iter(pipe._ba_ws))[1] if full3d and pipe._ba_ws else min(T * world, pipe.ba_max_frames or T * world)
+    sharded_ba = bool(full3d and world > 1 and args.ba_solver == "exact" and ops.ba_sharded_plan(CAMS, ba_frames, 38, world) is not None)
+    launches = int(pipe.launches(n_img, sharded_ba=sharded_ba) + 4) if full3d else int(pipe.engine.launches(n_img))
     line = {
         "metric": "7-cam frames/sec -> 3D pose", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps,
@@ -543,7 +550,7 @@ def run_b200(args):
         "clocks": clocks,
     }
     if rep is not None:
-        line["bundle_adjust"] = {"frames": min(T * world, pipe.ba_max_frames or T * world), "observations": rep["n_obs"],
+        line["bundle_adjust"] = {"frames": ba_frames, "sharded": sharded_ba, "observations": rep["n_obs"],
                                  "evaluations": rep["iters"], "accepted": rep["accepted"], "status": rep["status"],
                                  "solver": args.ba_solver, "device_ms_by_solver": ba_ms}
     if rank == 0:

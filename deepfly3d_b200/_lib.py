@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdf3d_b200.so")
 
 DF3D_MAX_CAMS = 8
+DF3D_EUNSUPPORTED = -4
 
 
 class BAOpts(C.Structure):
@@ -49,6 +50,11 @@ SIGNATURES = {
     "df3d_bundle_adjust_workspace_bytes": (_sz, [_i, _i, _i]),
     "df3d_bundle_adjust": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(BAOpts), _vp, _vp, _vp, _sz, _vp]),
     "df3d_bundle_adjust_launches": (_i, [C.POINTER(BAOpts)]),
+    "df3d_ba_sharded_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_sz), C.POINTER(_i)]),
+    "df3d_ba_sharded_begin": (_i, [_vp, _i, _i, _i, C.POINTER(BAOpts), _vp, _sz, _vp]),
+    "df3d_ba_sharded_pass": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "df3d_ba_sharded_finish": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "df3d_ba_sharded_end": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "df3d_reprojection_error": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "df3d_procrustes_workspace_bytes": (_sz, [_i]),
     "df3d_procrustes": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),

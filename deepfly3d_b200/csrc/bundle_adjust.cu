@@ -89,7 +89,21 @@ struct BAWorkspace {  // carved out of the caller's buffer
   double* lh;              // TJ*3
   double* lhb;             // TJ*3
   double* lpart;           // 2 * kBAMaxBlocks * kLsmrRed
+  // Block space of the per-point passes: a launch covers the virtual blocks [vb0, vb0 + gridDim.x) of `vgrid`.  One GPU:
+  // vb0 = 0, gridDim.x = vgrid and the last block to finish sums the per-block partials.  Frame-sharded (`sharded`): each
+  // rank launches its own slice of the blocks, the caller all-gathers the partials and ba_finish_kernel does the sum --
+  // same blocks, same order, same bits as on one GPU.
+  int vb0, vgrid, sharded, pad;
 };
+
+__device__ void gradient_tail(int C, BAWorkspace ws);
+__device__ void backsub_tail(int C, BAWorkspace ws);
+__device__ void step_tail(int C, BAWorkspace ws, const double* s_cn);
+
+static int ba_grid(int TJ) {
+  int g = ceil_div(TJ, kBAThreads);
+  return g < 1 ? 1 : (g > kBAMaxBlocks ? kBAMaxBlocks : g);
+}
 
 static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* ws) {
   size_t off = 0;
@@ -121,14 +135,14 @@ static size_t ba_workspace_layout(int C, int T, int J, char* base, BAWorkspace* 
   w.lh = reinterpret_cast<double*>(take(TJ * 3 * 8));
   w.lhb = reinterpret_cast<double*>(take(TJ * 3 * 8));
   w.lpart = reinterpret_cast<double*>(take((size_t)2 * kBAMaxBlocks * kLsmrRed * 8));
+  w.vb0 = 0;
+  w.vgrid = ba_grid((int)TJ);
+  w.sharded = 0;
+  w.pad = 0;
   if (ws) *ws = w;
   return off;
 }
 
-static int ba_grid(int TJ) {
-  int g = ceil_div(TJ, kBAThreads);
-  return g < 1 ? 1 : (g > kBAMaxBlocks ? kBAMaxBlocks : g);
-}
 
 // ---------------------------------------------------------------------------------------------
 __global__ void ba_begin_kernel(const double* __restrict__ cam_rt, int C, df3d_ba_opts opts, BAWorkspace ws) {
@@ -239,6 +253,18 @@ __device__ __forceinline__ void point_M(unsigned mask, const double (&V)[3][3], 
 // Last-block-done reduction of per-block partial vectors: entries [0, n_sum) are summed, [n_sum, n) take the
 // maximum, both in a fixed block order.  Returns true in every thread of the last block, after `out` is
 // complete and visible to it.
+// fixed-order sum (entries [0, n_sum)) / maximum (entries [n_sum, n)) of the partial vectors of `nblocks` blocks
+__device__ __forceinline__ void sum_block_partials(const double* partials, int n_sum, int n, double* out, unsigned nblocks) {
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    double acc = e < n_sum ? 0.0 : -1.0;
+    if (e < n_sum) {
+      for (unsigned b = 0; b < nblocks; ++b) acc += partials[(size_t)b * n + e];
+    } else {
+      for (unsigned b = 0; b < nblocks; ++b) acc = fmax(acc, partials[(size_t)b * n + e]);
+    }
+    out[e] = acc;
+  }
+}
 __device__ __forceinline__ bool reduce_partials_last_block(const double* partials, int n_sum, int n, double* out,
                                                            unsigned int* ticket) {
   __shared__ bool s_last;
@@ -251,15 +277,7 @@ __device__ __forceinline__ bool reduce_partials_last_block(const double* partial
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    double acc = e < n_sum ? 0.0 : -1.0;
-    if (e < n_sum) {
-      for (unsigned b = 0; b < gridDim.x; ++b) acc += partials[(size_t)b * n + e];
-    } else {
-      for (unsigned b = 0; b < gridDim.x; ++b) acc = fmax(acc, partials[(size_t)b * n + e]);
-    }
-    out[e] = acc;
-  }
+  sum_block_partials(partials, n_sum, n, out, gridDim.x);
   if (threadIdx.x == 0) *ticket = 0u;
   __threadfence();
   __syncthreads();
@@ -376,7 +394,7 @@ ba_gradient_kernel(const double* __restrict__ intr, const double2* __restrict__ 
   double* aw = my + g_off_w(C);
   double* asc = my + g_off_sc(C);
 
-  for (int base = blockIdx.x * kBAThreads; base < TJ; base += gridDim.x * kBAThreads) {
+  for (int base = (blockIdx.x + ws.vb0) * kBAThreads; base < TJ; base += ws.vgrid * kBAThreads) {
     const int g = base + threadIdx.x;
     const bool valid = g < TJ;
     double X[3] = {0.0, 0.0, 0.0};
@@ -477,10 +495,16 @@ ba_gradient_kernel(const double* __restrict__ intr, const double2* __restrict__ 
       asc[5] = fmax(asc[5], gm);
     }
   }
-  block_partial(s_t, n_sum, n, ws.partials + (size_t)blockIdx.x * n);
+  block_partial(s_t, n_sum, n, ws.partials + (size_t)(blockIdx.x + ws.vb0) * n);
+  if (ws.sharded) return;  // the partials are all-gathered first, ba_finish_kernel goes on from here
   if (!reduce_partials_last_block(ws.partials, n_sum, n, ws.red, ws.counters + 0)) return;
-  if (threadIdx.x != 0) return;
-  // ---- last block, one thread: camera scaling, gradient norms, Cauchy-step regularisation
+  if (threadIdx.x == 0) gradient_tail(C, ws);
+}
+
+// ---- after the reduction, one thread: camera scaling, gradient norms, Cauchy-step regularisation
+__device__ void gradient_tail(int C, BAWorkspace ws) {
+  BAState* st = ws.state;
+  const bool first = st->first != 0;
   const double* red = ws.red;
   const double* U = red + g_off_U(C);
   const double* gc = red + g_off_gc(C);
@@ -561,7 +585,7 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
   double* aS = my + off_S(C);
   double* ab = my + off_b(C);
 
-  for (int base = blockIdx.x * kBAThreads; base < TJ; base += gridDim.x * kBAThreads) {
+  for (int base = (blockIdx.x + ws.vb0) * kBAThreads; base < TJ; base += ws.vgrid * kBAThreads) {
     const int g = base + threadIdx.x;
     const bool valid = g < TJ;
     double X[3] = {0.0, 0.0, 0.0};
@@ -662,7 +686,8 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
       }
     }
   }
-  block_partial(s_sys, nsys, nsys, ws.partials + (size_t)blockIdx.x * nsys);
+  block_partial(s_sys, nsys, nsys, ws.partials + (size_t)(blockIdx.x + ws.vb0) * nsys);
+  if (ws.sharded) return;
   reduce_partials_last_block(ws.partials, nsys, nsys, ws.red, ws.counters + 1);
 }
 
@@ -775,7 +800,7 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
   __syncthreads();
 
   double a_ggn = 0.0, a_gngn = 0.0, a_JgJgn = 0.0, a_JgnJgn = 0.0;
-  for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += gridDim.x * kBAThreads) {
+  for (int g = (blockIdx.x + ws.vb0) * kBAThreads + threadIdx.x; g < TJ; g += ws.vgrid * kBAThreads) {
     const double X[3] = {pts3d[(size_t)g * 3 + 0], pts3d[(size_t)g * 3 + 1], pts3d[(size_t)g * 3 + 2]};
     double V[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     double rp[3] = {0, 0, 0};  // sum Jp^T (r - Jc dcn)
@@ -860,10 +885,15 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
     s_t[warp * 4 + 2] = a_JgJgn;
     s_t[warp * 4 + 3] = a_JgnJgn;
   }
-  block_partial(s_t, 4, 4, ws.partials + (size_t)blockIdx.x * 4);
+  block_partial(s_t, 4, 4, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 4);
+  if (ws.sharded) return;
   if (!reduce_partials_last_block(ws.partials, 4, 4, ws.red, ws.counters + 2)) return;
-  if (threadIdx.x != 0) return;
-  // ---- last block, one thread: the 2-D sub-problem in an orthonormal basis of span{g_h, gn_h}
+  if (threadIdx.x == 0) backsub_tail(C, ws);
+}
+
+// ---- after the reduction, one thread: the 2-D sub-problem in an orthonormal basis of span{g_h, gn_h}
+__device__ void backsub_tail(int C, BAWorkspace ws) {
+  BAState* st = ws.state;
   double g_gn = ws.red[0], gn_gn = ws.red[1];
   const double Jg_Jgn = ws.red[2], Jgn_Jgn = ws.red[3];
   for (int i = 0; i < 6 * C; ++i) {
@@ -1338,7 +1368,7 @@ ba_step_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
   __syncthreads();
 
   double cost = 0.0, stepsq = 0.0, xsq = 0.0;
-  for (int g = blockIdx.x * kBAThreads + threadIdx.x; g < TJ; g += gridDim.x * kBAThreads) {
+  for (int g = (blockIdx.x + ws.vb0) * kBAThreads + threadIdx.x; g < TJ; g += ws.vgrid * kBAThreads) {
     double Xn[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -1366,10 +1396,15 @@ ba_step_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
     s_t[warp * 3 + 1] = stepsq;
     s_t[warp * 3 + 2] = xsq;
   }
-  block_partial(s_t, 3, 3, ws.partials + (size_t)blockIdx.x * 3);
+  block_partial(s_t, 3, 3, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 3);
+  if (ws.sharded) return;
   if (!reduce_partials_last_block(ws.partials, 3, 3, ws.red, ws.counters + 3)) return;
-  if (threadIdx.x != 0) return;
-  // ---- last block, one thread: trf_no_bounds' inner loop body after f_new = fun(x_new)
+  if (threadIdx.x == 0) step_tail(C, ws, s_cn);
+}
+
+// ---- after the reduction, one thread: trf_no_bounds' inner loop body after f_new = fun(x_new); s_cn = the candidate cameras
+__device__ void step_tail(int C, BAWorkspace ws, const double* s_cn) {
+  BAState* st = ws.state;
   const double Fn = ws.red[0];
   double stepsq_t = ws.red[1], xsq_t = ws.red[2];
   for (int i = 0; i < 6 * C; ++i) {
@@ -1418,9 +1453,40 @@ ba_step_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
 }
 
 // accept_flag holds the number of the iteration whose candidate was accepted (0: none)
-__global__ void ba_apply_points_kernel(int n, int iter, BAWorkspace ws, double* __restrict__ pts3d) {
+// (frame-sharded: only the points of this rank's blocks have a candidate; `nb` = blocks of this rank)
+__global__ void ba_apply_points_kernel(int n, int iter, BAWorkspace ws, double* __restrict__ pts3d, int nb) {
   if (ws.state->accept_flag != iter) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pts3d[i] = ws.X_new[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (ws.sharded) {
+      const int vb = ((i / 3) / kBAThreads) % ws.vgrid;  // the block whose grid-stride loop owns this point
+      if (vb < ws.vb0 || vb >= ws.vb0 + nb) continue;
+    }
+    pts3d[i] = ws.X_new[i];
+  }
+}
+
+// Frame-sharded runs: what the last block of a per-point pass does on one GPU, after the caller has all-gathered the
+// per-block partials of every rank.  One block.  pass 0 gradient, 1 Schur system, 2 back-substitution, 3 step.
+__global__ void __launch_bounds__(kBAThreads) ba_finish_kernel(int pass, int C, BAWorkspace ws) {
+  __shared__ double s_cn[kMaxN];
+  BAState* st = ws.state;
+  if (st->done) return;
+  if (pass != 3 && !st->need_lin) return;
+  if (pass == 1 && st->solver == 1) return;
+  if (pass == 3) {  // the candidate cameras, as ba_step_kernel builds them
+    const double cg = st->coef_g, cn = st->coef_gn;
+    if (threadIdx.x < 6 * C)
+      s_cn[threadIdx.x] = ws.cam[threadIdx.x] + (cg * ws.ghc[threadIdx.x] + cn * ws.gnc[threadIdx.x]) / ws.sinv_c[threadIdx.x];
+  }
+  const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
+  const int n_sum = pass == 0 ? n - 1 : n;
+  sum_block_partials(ws.partials, n_sum, n, ws.red, (unsigned)ws.vgrid);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (pass == 0) gradient_tail(C, ws);
+  if (pass == 2) backsub_tail(C, ws);
+  if (pass == 3) step_tail(C, ws, s_cn);
 }
 
 __global__ void ba_end_kernel(double* __restrict__ cam_rt, int C, BAWorkspace ws, df3d_ba_report* report) {
@@ -1546,10 +1612,115 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
     }
     ba_backsub_kernel<<<grid, kBAThreads, smem_b, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
     ba_step_kernel<<<grid, kBAThreads, smem_e, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
-    ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, it + 1, ws, pts3d_dev);
+    ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, it + 1, ws, pts3d_dev, 0);
     DF3D_LAUNCH_CHECK("bundle adjustment iteration");
   }
   ba_end_kernel<<<1, 64, 0, s>>>(cam_rt_dev, C, ws, report_dev);
+  DF3D_LAUNCH_CHECK("ba_end_kernel");
+  return DF3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame-sharded form of df3d_bundle_adjust (solver 0), see include/df3d_b200.h.
+static int ba_pass_doubles(int pass, int C) { return pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3; }
+
+extern "C" int df3d_ba_sharded_plan(int C, int T, int J, int world, int* n_blocks, size_t* partials_offset, int* pass_doubles) {
+  if (int e = check_common("df3d_ba_sharded_plan", C, T, J)) return e;
+  DF3D_REQUIRE(n_blocks && partials_offset && pass_doubles && world >= 1, DF3D_EINVAL, "df3d_ba_sharded_plan: bad arguments");
+  const int grid = ba_grid(T * J);
+  DF3D_REQUIRE(grid % world == 0, DF3D_EUNSUPPORTED,
+               "df3d_ba_sharded_plan: %d blocks of points do not split evenly over %d ranks (solve replicated instead)", grid, world);
+  BAWorkspace ws;
+  ba_workspace_layout(C, T, J, reinterpret_cast<char*>(uintptr_t(256)), &ws);  // offsets relative to a fictitious base
+  *n_blocks = grid;
+  *partials_offset = reinterpret_cast<uintptr_t>(ws.partials) - 256;
+  for (int p = 0; p < 4; ++p) pass_doubles[p] = ba_pass_doubles(p, C);
+  return DF3D_OK;
+}
+
+static int ba_sharded_ws(const char* fn, int C, int T, int J, void* workspace_dev, size_t workspace_bytes, int rank, int world,
+                         BAWorkspace* ws, int* nb) {
+  if (int e = check_common(fn, C, T, J)) return e;
+  DF3D_REQUIRE(workspace_dev && (reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, DF3D_EINVAL, "%s: workspace must be 256-byte aligned", fn);
+  const size_t need = ba_workspace_layout(C, T, J, static_cast<char*>(workspace_dev), ws);
+  DF3D_REQUIRE(workspace_bytes >= need, DF3D_ENOMEM, "%s: workspace too small (%zu < %zu bytes)", fn, workspace_bytes, need);
+  DF3D_REQUIRE(world >= 1 && rank >= 0 && rank < world && ws->vgrid % world == 0, DF3D_EINVAL, "%s: rank %d of %d over %d blocks", fn, rank,
+               world, ws->vgrid);
+  *nb = ws->vgrid / world;
+  ws->vb0 = rank * *nb;
+  ws->sharded = 1;
+  return DF3D_OK;
+}
+
+extern "C" int df3d_ba_sharded_begin(const double* cam_rt_dev, int C, int T, int J, const df3d_ba_opts* opts, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+  BAWorkspace ws;
+  int nb;
+  if (int e = ba_sharded_ws("df3d_ba_sharded_begin", C, T, J, workspace_dev, workspace_bytes, 0, 1, &ws, &nb)) return e;
+  DF3D_REQUIRE(cam_rt_dev, DF3D_EINVAL, "df3d_ba_sharded_begin: null pointer");
+  df3d_ba_opts o{20, 1e-4, 1e-8, 1e-8, 0};
+  if (opts) o = *opts;
+  DF3D_REQUIRE(o.max_iters >= 1 && o.max_iters <= 1000 && o.ftol >= 0.0 && o.xtol >= 0.0 && o.gtol >= 0.0 && o.solver == 0, DF3D_EINVAL,
+               "df3d_ba_sharded_begin: bad options (max_iters in [1,1000], tolerances >= 0, solver 0: the LSMR solver runs replicated)");
+  ba_begin_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(cam_rt_dev, C, o, ws);
+  DF3D_LAUNCH_CHECK("ba_begin_kernel");
+  return DF3D_OK;
+}
+
+extern "C" int df3d_ba_sharded_pass(int pass, int rank, int world, const double* intr_dev, const double* pts_xy_dev, const double* pts3d_dev,
+                                    int C, int T, int J, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  BAWorkspace ws;
+  int nb;
+  if (int e = ba_sharded_ws("df3d_ba_sharded_pass", C, T, J, workspace_dev, workspace_bytes, rank, world, &ws, &nb)) return e;
+  DF3D_REQUIRE(pass >= 0 && pass <= 3 && intr_dev && pts_xy_dev && pts3d_dev, DF3D_EINVAL, "df3d_ba_sharded_pass: bad arguments");
+  DF3D_REQUIRE((reinterpret_cast<uintptr_t>(pts_xy_dev) & 15) == 0, DF3D_EINVAL, "df3d_ba_sharded_pass: pts_xy must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int TJ = T * J;
+  const double2* xy = reinterpret_cast<const double2*>(pts_xy_dev);
+  const size_t smem_g = ((size_t)C * kCamStride + (size_t)kBAWarps * g_doubles(C)) * sizeof(double);
+  const size_t smem_s = ((size_t)C * kCamStride + (size_t)kBAWarps * sys_doubles(C)) * sizeof(double);
+  const size_t smem_b = ((size_t)C * kCamStride + 12 * C + kBAWarps * 4) * sizeof(double);
+  const size_t smem_e = ((size_t)C * kCamStride + 6 * C + kBAWarps * 3) * sizeof(double);
+  if (pass == 0) ba_gradient_kernel<<<nb, kBAThreads, smem_g, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+  if (pass == 1) {
+    DF3D_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    ba_schur_kernel<<<nb, kBAThreads, smem_s, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+  }
+  if (pass == 2) ba_backsub_kernel<<<nb, kBAThreads, smem_b, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+  if (pass == 3) ba_step_kernel<<<nb, kBAThreads, smem_e, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+  DF3D_LAUNCH_CHECK("bundle adjustment pass");
+  return DF3D_OK;
+}
+
+// after the all-gather of the pass's partials: the fixed-order sum over ALL blocks and the scalar logic behind it; behind
+// pass 1 the reduced camera system is solved, behind pass 3 (of iteration `iter`, counted from 1) an accepted candidate
+// replaces this rank's points
+extern "C" int df3d_ba_sharded_finish(int pass, int iter, int rank, int world, double* pts3d_dev, int C, int T, int J, void* workspace_dev,
+                                      size_t workspace_bytes, void* stream) {
+  BAWorkspace ws;
+  int nb;
+  if (int e = ba_sharded_ws("df3d_ba_sharded_finish", C, T, J, workspace_dev, workspace_bytes, rank, world, &ws, &nb)) return e;
+  DF3D_REQUIRE(pass >= 0 && pass <= 3 && pts3d_dev, DF3D_EINVAL, "df3d_ba_sharded_finish: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ba_finish_kernel<<<1, kBAThreads, 0, s>>>(pass, C, ws);
+  if (pass == 1) ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
+  if (pass == 3) {
+    const int n3 = T * J * 3;
+    int agrid = ceil_div(n3, 256);
+    if (agrid > 4 * kBAMaxBlocks) agrid = 4 * kBAMaxBlocks;
+    ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, iter, ws, pts3d_dev, nb);
+  }
+  DF3D_LAUNCH_CHECK("bundle adjustment finish");
+  return DF3D_OK;
+}
+
+extern "C" int df3d_ba_sharded_end(double* cam_rt_dev, int C, int T, int J, df3d_ba_report* report_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream) {
+  BAWorkspace ws;
+  int nb;
+  if (int e = ba_sharded_ws("df3d_ba_sharded_end", C, T, J, workspace_dev, workspace_bytes, 0, 1, &ws, &nb)) return e;
+  DF3D_REQUIRE(cam_rt_dev, DF3D_EINVAL, "df3d_ba_sharded_end: null pointer");
+  ba_end_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(cam_rt_dev, C, ws, report_dev);
   DF3D_LAUNCH_CHECK("ba_end_kernel");
   return DF3D_OK;
 }

@@ -194,6 +194,65 @@ def bundle_adjust(cam_rt, intr4, pts_xy, pts3d, max_iters=20, ftol=1e-4, xtol=1e
     return rep
 
 
+def ba_sharded_plan(Cn, T, J, world):
+    """-> (n_blocks, partials_offset_bytes, [doubles per block of pass 0..3]) or None when the blocks of points do not
+    split evenly over `world` ranks (the caller then solves replicated)."""
+    nb, off, pd = C.c_int(), C.c_size_t(), (C.c_int * 4)()
+    rc = lib.df3d_ba_sharded_plan(int(Cn), int(T), int(J), int(world), C.byref(nb), C.byref(off), pd)
+    if rc == _lib.DF3D_EUNSUPPORTED:
+        return None
+    check(rc)
+    return nb.value, off.value, list(pd)
+
+
+def bundle_adjust_sharded(cam_rt, intr4, pts_xy, pts3d, group=None, max_iters=20, ftol=1e-4, xtol=1e-8, gtol=1e-8, workspace=None,
+                          ranks=None):
+    """Frame-sharded bundle adjustment (exact solver): every rank of `group` calls this with the SAME cameras and the SAME
+    gathered 2-D points; the per-point work of each pass is split by blocks of points between the ranks, the per-block
+    partial sums are all-gathered (one `all_gather_into_tensor` per pass) and summed in the single-GPU order, so cam_rt
+    comes out bit-identical to ``bundle_adjust(..., solver="exact")`` on one GPU -- at 1 / world of its per-point work.
+    pts3d: only the points of this rank's blocks are updated.  `ranks` = (rank, world) without a process group runs the
+    passes of all `world` ranks one after the other on this GPU (tests)."""
+    import torch.distributed as dist
+
+    _need_cuda(cam_rt, intr4, pts_xy, pts3d)
+    for t in (cam_rt, intr4, pts_xy, pts3d):
+        if t.dtype != torch.float64 or not t.is_contiguous():
+            raise ValueError("bundle_adjust_sharded: contiguous float64 tensors required")
+    Cn, T, J, _ = pts_xy.shape
+    if group is not None:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        local = [rank]
+    else:
+        world = int(ranks) if ranks else 1
+        rank, local = 0, list(range(world))
+    plan = ba_sharded_plan(Cn, T, J, world)
+    if plan is None:
+        raise ValueError("bundle_adjust_sharded: the point blocks do not split evenly over the ranks")
+    n_blocks, off, pass_doubles = plan
+    ws = workspace if workspace is not None else ba_workspace(Cn, T, J, cam_rt.device)
+    wp, wn = _aligned_ptr(ws)
+    base = wp.value - ws.data_ptr() + off                       # byte offset of the partials inside the workspace tensor
+    opts = _lib.BAOpts(int(max_iters), float(ftol), float(xtol), float(gtol), 0)
+    rep = torch.zeros(C.sizeof(_lib.BAReport), dtype=torch.uint8, device=cam_rt.device)
+    st = _stream()
+    check(lib.df3d_ba_sharded_begin(_ptr(cam_rt), Cn, T, J, C.byref(opts), wp, wn, st))
+    per = n_blocks // world
+    for it in range(1, int(max_iters) + 1):
+        for p in range(4):
+            for r in local:
+                check(lib.df3d_ba_sharded_pass(p, r, world, _ptr(intr4), _ptr(pts_xy), _ptr(pts3d), Cn, T, J, wp, wn, st))
+            if group is not None and world > 1:
+                region = ws[base:base + n_blocks * pass_doubles[p] * 8].view(torch.float64)
+                mine = region[rank * per * pass_doubles[p]:(rank + 1) * per * pass_doubles[p]].clone()
+                dist.all_gather_into_tensor(region, mine, group=group)
+            # (without a process group all blocks were computed here: one finish that owns every point)
+            fr, fw = (rank, world) if group is not None else (0, 1)
+            check(lib.df3d_ba_sharded_finish(p, it, fr, fw, _ptr(pts3d), Cn, T, J, wp, wn, st))
+    check(lib.df3d_ba_sharded_end(_ptr(cam_rt), Cn, T, J, _ptr(rep), wp, wn, st))
+    return rep
+
+
 def bundle_adjust_launches(max_iters, solver="lsmr"):
     opts = _lib.BAOpts(int(max_iters), 1e-4, 1e-8, 1e-8, 1 if solver == "lsmr" else 0)
     return int(lib.df3d_bundle_adjust_launches(C.byref(opts)))

@@ -7,9 +7,12 @@ reference (df3d/core.py:170-203, 229-250, 351-360) minus file I/O, and what benc
 Multi-GPU (one process per GPU, ``group`` = the NCCL process group): frames shard in contiguous blocks, all
 7 cameras of a frame on one rank.  Hourglass, arg-max, packing and DLT need no communication.  Bundle
 adjustment is ONE global problem over all frames (42 shared camera unknowns): the packed 2-D
-points of the frames it uses (4 256 B / frame) are all-gathered, every rank solves the same problem with the
-same bit-reproducible kernels and ends with identical cameras -- no collective inside the solver -- then
-triangulates its own frames; one all-gather of the 3-D joints (912 B / frame) ends the step.
+points of the frames it uses (4 256 B / frame) are all-gathered and every rank ends with identical cameras.  With
+the LSMR solver every rank solves the whole problem with the same bit-reproducible kernels (no collective inside the
+solver); with the exact solver the per-point work of each pass is split by blocks of points between the ranks and
+the per-block partial sums are all-gathered and summed in the single-GPU order (ops.bundle_adjust_sharded) -- in
+both cases the cameras equal the single-GPU ones to the bit.  Each rank then triangulates its own frames; one
+all-gather of the 3-D joints (912 B / frame) ends the step.
 """
 import numpy as np
 import torch
@@ -101,8 +104,19 @@ class Pose3DPipeline:
         key = (Cn, ba_xy.shape[1], J)
         if key not in self._ba_ws:
             self._ba_ws[key] = ops.ba_workspace(*key, self.device)
-        rep = ops.bundle_adjust(cam, self.intr4, ba_xy, X, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
-                                workspace=self._ba_ws[key], solver=self.ba_solver)
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(group)
+        if world > 1 and self.ba_solver == "exact" and ops.ba_sharded_plan(*key, world) is not None:
+            # the per-point work of every pass split between the ranks, per-block partial sums all-gathered and summed in
+            # the single-GPU order: same cameras to the bit, 1 / world of the work (the LSMR solver runs replicated)
+            rep = ops.bundle_adjust_sharded(cam, self.intr4, ba_xy, X, group=group, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
+                                            workspace=self._ba_ws[key])
+        else:
+            rep = ops.bundle_adjust(cam, self.intr4, ba_xy, X, max_iters=self.ba_max_iters, ftol=self.ba_ftol,
+                                    workspace=self._ba_ws[key], solver=self.ba_solver)
         P1, R1 = ops.projection_matrices(cam, self.intr4)
         X1 = ops.triangulate_dlt(P1, pxy)                        # own frames only
         return cam, R1, X1, rep
@@ -113,10 +127,11 @@ class Pose3DPipeline:
         return {"idx": idx, "conf": conf, "points2d": p2d, "pts_xy": pxy, "cam_rt": cam, "R": R1,
                 "points3d_wo_procrustes": X1, "ba_report": rep}
 
-    def launches(self, n_images):
+    def launches(self, n_images, sharded_ba=False):
         """Kernel launches of one `run` (for bench.py's gpu_launches): hourglass plan + pack + 2 x
-        (projection + DLT) + bundle adjustment."""
-        return self.engine.launches(n_images) + 1 + 4 + ops.bundle_adjust_launches(self.ba_max_iters, self.ba_solver)
+        (projection + DLT) + bundle adjustment (sharded exact solver: per iteration 4 passes + 4 finishes + solve + apply)."""
+        ba = 2 + 10 * self.ba_max_iters if sharded_ba else ops.bundle_adjust_launches(self.ba_max_iters, self.ba_solver)
+        return self.engine.launches(n_images) + 1 + 4 + ba
 
 
 def gather_frames(x, group=None, dim=0):

@@ -175,6 +175,27 @@ int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, const double*
 /* kernels one df3d_bundle_adjust call launches (for bench.py's gpu_launches) */
 int df3d_bundle_adjust_launches(const df3d_ba_opts* opts);
 
+/* Frame-sharded form of df3d_bundle_adjust for solver 0 (one process per GPU, the bundle adjustment is
+ * ONE problem over the frames of all ranks).  Every rank holds the same cameras, 2-D points and workspace layout; the
+ * per-point work of each of the four passes of an iteration (0 gradient, 1 Schur system, 2 back-substitution, 3 candidate
+ * step) is split by blocks of points: rank r runs blocks [r n_blocks / world, (r+1) n_blocks / world) and writes their
+ * partial sums; the CALLER all-gathers the partials (torch.distributed / NCCL -- the library holds no communicator):
+ * region [partials_offset, + n_blocks * pass_doubles[pass] * 8) of the workspace, rank r's slice being its blocks;
+ * df3d_ba_sharded_finish then sums ALL blocks in the fixed order the single-GPU solver uses.  Same blocks, same order:
+ * the cameras are bit-identical to df3d_bundle_adjust on one GPU, on every rank.  pts3d_dev: only the points of the
+ * rank's own blocks are updated.  Sequence: begin; per iteration 1..max_iters: for pass 0..3 { pass; all-gather;
+ * finish(pass, iteration) }; end.  df3d_ba_sharded_plan fails with DF3D_EUNSUPPORTED when the blocks do not split
+ * evenly over `world` (run df3d_bundle_adjust replicated then). */
+int df3d_ba_sharded_plan(int C, int T, int J, int world, int* n_blocks, size_t* partials_offset, int* pass_doubles /* [4] */);
+int df3d_ba_sharded_begin(const double* cam_rt_dev, int C, int T, int J, const df3d_ba_opts* opts, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+int df3d_ba_sharded_pass(int pass, int rank, int world, const double* intr_dev, const double* pts_xy_dev,
+                         const double* pts3d_dev, int C, int T, int J, void* workspace_dev, size_t workspace_bytes, void* stream);
+int df3d_ba_sharded_finish(int pass, int iter, int rank, int world, double* pts3d_dev, int C, int T, int J, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
+int df3d_ba_sharded_end(double* cam_rt_dev, int C, int T, int J, df3d_ba_report* report_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream);
+
 /* Mean L2 reprojection error in pixels (pyba CameraNetwork.reprojection_error(), printed at
  * df3d/core.py:250).  out_dev: 2 float64 = {sum of distances, number of observations}. */
 int df3d_reprojection_error(const double* cam_rt_dev, const double* intr_dev,

@@ -212,18 +212,23 @@ def _sharded_worker(rank, world, port, T, out_dir):
 
     full = ohg.to_uint8(ohg.synthetic_images(7 * T, 128, 128, seed=5)).view(7, T, 128, 128)
     lo, hi = shard_frames(T, rank, world)
-    pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * (hi - lo), image_shape=[960, 480], device=f"cuda:{rank}")
-    out = pipe.run(full[:, lo:hi].reshape(7 * (hi - lo), 128, 128).cuda(), hi - lo, group=dist.group.WORLD)
-    x3d = gather_frames(out["points3d_wo_procrustes"], dist.group.WORLD)
-    torch.cuda.synchronize()
-    torch.save({"x3d": x3d.cpu(), "cam": out["cam_rt"].cpu(), "idx": out["idx"].cpu(), "range": (lo, hi)},
-               os.path.join(out_dir, f"r{rank}.pt"))
+    res = {"range": (lo, hi)}
+    for solver in ("lsmr", "exact"):                 # replicated LSMR solve / exact solve with the per-point work sharded
+        pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * (hi - lo), image_shape=[960, 480], device=f"cuda:{rank}",
+                              ba_solver=solver)
+        out = pipe.run(full[:, lo:hi].reshape(7 * (hi - lo), 128, 128).cuda(), hi - lo, group=dist.group.WORLD)
+        x3d = gather_frames(out["points3d_wo_procrustes"], dist.group.WORLD)
+        torch.cuda.synchronize()
+        res[solver] = {"x3d": x3d.cpu(), "cam": out["cam_rt"].cpu(), "idx": out["idx"].cpu()}
+        del pipe
+    torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
 def test_sharded_two_gpus_equals_single_gpu(tmp_path, lib_built):
-    """Frame-sharded run over NCCL (2 ranks: all-gather of the 2-D points, replicated bundle adjustment, local
-    DLT, all-gather of the 3-D joints) == the single-GPU run on the concatenated frames, bit for bit."""
+    """Frame-sharded run over NCCL (2 ranks: all-gather of the 2-D points, bundle adjustment -- replicated with the LSMR
+    solver, per-point work sharded + per-block partials all-gathered with the exact one --, local DLT, all-gather of
+    the 3-D joints) == the single-GPU run on the concatenated frames, bit for bit."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import socket
@@ -237,18 +242,23 @@ def test_sharded_two_gpus_equals_single_gpu(tmp_path, lib_built):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    T = 12
+    T = 26                                           # 26 x 38 = 988 points = 8 blocks of 128: splits over 2 ranks
+    from deepfly3d_b200 import ops
+
+    assert ops.ba_sharded_plan(7, T, 38, 2) is not None
     mp.spawn(_sharded_worker, args=(2, port, T, str(tmp_path)), nprocs=2, join=True)
     full = ohg.to_uint8(ohg.synthetic_images(7 * T, 128, 128, seed=5))
-    pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * T, image_shape=[960, 480])
-    ref = pipe.run(full.cuda(), T)
-    torch.cuda.synchronize()
-    for r in range(2):
-        d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
-        lo, hi = d["range"]
-        assert torch.equal(d["idx"], ref["idx"].cpu().view(7, T, -1)[:, lo:hi].reshape(7 * (hi - lo), -1))
-        assert torch.equal(d["cam"], ref["cam_rt"].cpu()), "replicated bundle adjustment differs from the single-GPU solve"
-        assert torch.equal(d["x3d"], ref["points3d_wo_procrustes"].cpu())
+    for solver in ("lsmr", "exact"):
+        pipe = Pose3DPipeline(random_state_dict(2, seed=0), 128, 128, 7 * T, image_shape=[960, 480], ba_solver=solver)
+        ref = pipe.run(full.cuda(), T)
+        torch.cuda.synchronize()
+        for r in range(2):
+            d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+            lo, hi = d["range"]
+            assert torch.equal(d[solver]["idx"], ref["idx"].cpu().view(7, T, -1)[:, lo:hi].reshape(7 * (hi - lo), -1))
+            assert torch.equal(d[solver]["cam"], ref["cam_rt"].cpu()), f"{solver}: multi-GPU bundle adjustment differs from the single-GPU solve"
+            assert torch.equal(d[solver]["x3d"], ref["points3d_wo_procrustes"].cpu())
+        del pipe
 
 
 def test_core_streams_videos_without_expanding_them(tmp_path, lib_built):

@@ -291,6 +291,46 @@ def test_bundle_adjust_is_bit_reproducible(ops):
         assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
 
 
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_bundle_adjust_equals_the_single_gpu_solve(ops, world):
+    """The frame-sharded form of the exact solver (per-point work split by blocks of points, per-block partial sums
+    summed in the single-GPU order after an all-gather): here the passes of all `world` ranks run one after the other on
+    one GPU into the same workspace -- what the all-gather produces -- and must give the single-GPU cameras and points
+    bit for bit, on a perturbed start that takes several accepted and rejected steps."""
+    from deepfly3d_b200.ops import intr_to_vec4
+    from oracle import synth
+
+    T = 64                                                        # 64 x 38 points = 19 blocks of 128 -> not divisible
+    calib, pts, _ = synth.config3_geometry(T, seed=11)
+    rng = np.random.default_rng(5)
+    cam0 = np.stack([np.concatenate([g.rodrigues_inv(calib["R"][k]), calib["tvec"][k]]) for k in range(7)])
+    cam0 = cam0 + rng.normal(0, 2e-3, cam0.shape)
+    intr4 = _cuda(intr_to_vec4(calib["intr"]))
+    if ops.ba_sharded_plan(7, T, 38, world) is None:
+        T = 64 + 4 * (world // 2)                                 # find a frame count whose blocks split evenly
+        while ops.ba_sharded_plan(7, T, 38, world) is None:
+            T += 1
+        calib, pts, _ = synth.config3_geometry(T, seed=11)
+    pxy = _cuda(pts)
+    outs = []
+    for sharded in (False, True):
+        cam = _cuda(cam0)
+        P0, _ = ops.projection_matrices(cam, intr4)
+        X = ops.triangulate_dlt(P0, pxy)
+        if sharded:
+            rep = ops.bundle_adjust_sharded(cam, intr4, pxy, X, ranks=world, max_iters=12)
+        else:
+            rep = ops.bundle_adjust(cam, intr4, pxy, X, max_iters=12, solver="exact")
+        outs.append((cam.cpu().numpy(), X.cpu().numpy(), ops.ba_report(rep)))
+    (c0, x0, r0), (c1, x1, r1) = outs
+    assert r0["iters"] >= 3 and r0 == r1, (r0, r1)
+    assert np.array_equal(c0, c1), f"cameras differ by {np.abs(c0 - c1).max()}"
+    assert np.array_equal(x0, x1)
+    assert ops.ba_sharded_plan(7, 3, 38, 4) is None              # 1 block of points over 4 ranks: refused, solve replicated
+    with pytest.raises(ValueError):
+        ops.bundle_adjust_sharded(_cuda(cam0), intr4, pxy[:, :3].contiguous(), X[:3].contiguous(), ranks=4)
+
+
 def test_errors_are_reported(ops):
     from deepfly3d_b200._lib import Df3dError
 
