@@ -250,40 +250,10 @@ __device__ __forceinline__ void point_M(unsigned mask, const double (&V)[3][3], 
   }
 }
 
-// Last-block-done reduction of per-block partial vectors: entries [0, n_sum) are summed, [n_sum, n) take the
-// maximum, both in a fixed block order.  Returns true in every thread of the last block, after `out` is
-// complete and visible to it.
-// fixed-order sum (entries [0, n_sum)) / maximum (entries [n_sum, n)) of the partial vectors of `nblocks` blocks
-__device__ __forceinline__ void sum_block_partials(const double* partials, int n_sum, int n, double* out, unsigned nblocks) {
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    double acc = e < n_sum ? 0.0 : -1.0;
-    if (e < n_sum) {
-      for (unsigned b = 0; b < nblocks; ++b) acc += partials[(size_t)b * n + e];
-    } else {
-      for (unsigned b = 0; b < nblocks; ++b) acc = fmax(acc, partials[(size_t)b * n + e]);
-    }
-    out[e] = acc;
-  }
-}
-__device__ __forceinline__ bool reduce_partials_last_block(const double* partials, int n_sum, int n, double* out,
-                                                           unsigned int* ticket) {
-  __shared__ bool s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-  sum_block_partials(partials, n_sum, n, out, gridDim.x);
-  if (threadIdx.x == 0) *ticket = 0u;
-  __threadfence();
-  __syncthreads();
-  return true;
-}
-
+// Every per-point pass ends with one partial vector per block (block_partial); ba_finish_kernel sums the blocks in block
+// order -- entries [0, n_sum) are summed, [n_sum, n) take the maximum -- one entry per thread, and its last block runs the
+// scalar logic that follows the pass.  (Round 2 first summed inside the last block of the pass itself: 592 blocks x
+// 2 102 doubles through ONE block cost ~0.6 ms per evaluation at 8 000 frames, two thirds of the whole solve.)
 // block partial = fixed-order sum (or max) of the per-warp tiles
 __device__ __forceinline__ void block_partial(const double* s_tiles, int n_sum, int n, double* part) {
   __syncthreads();
@@ -495,10 +465,7 @@ ba_gradient_kernel(const double* __restrict__ intr, const double2* __restrict__ 
       asc[5] = fmax(asc[5], gm);
     }
   }
-  block_partial(s_t, n_sum, n, ws.partials + (size_t)(blockIdx.x + ws.vb0) * n);
-  if (ws.sharded) return;  // the partials are all-gathered first, ba_finish_kernel goes on from here
-  if (!reduce_partials_last_block(ws.partials, n_sum, n, ws.red, ws.counters + 0)) return;
-  if (threadIdx.x == 0) gradient_tail(C, ws);
+  block_partial(s_t, n_sum, n, ws.partials + (size_t)(blockIdx.x + ws.vb0) * n);  // ba_finish_kernel(0) goes on from here
 }
 
 // ---- after the reduction, one thread: camera scaling, gradient norms, Cauchy-step regularisation
@@ -686,9 +653,7 @@ ba_schur_kernel(const double* __restrict__ intr, const double2* __restrict__ pts
       }
     }
   }
-  block_partial(s_sys, nsys, nsys, ws.partials + (size_t)(blockIdx.x + ws.vb0) * nsys);
-  if (ws.sharded) return;
-  reduce_partials_last_block(ws.partials, nsys, nsys, ws.red, ws.counters + 1);
+  block_partial(s_sys, nsys, nsys, ws.partials + (size_t)(blockIdx.x + ws.vb0) * nsys);  // ba_finish_kernel(1) sums them
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -885,10 +850,7 @@ ba_backsub_kernel(const double* __restrict__ intr, const double2* __restrict__ p
     s_t[warp * 4 + 2] = a_JgJgn;
     s_t[warp * 4 + 3] = a_JgnJgn;
   }
-  block_partial(s_t, 4, 4, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 4);
-  if (ws.sharded) return;
-  if (!reduce_partials_last_block(ws.partials, 4, 4, ws.red, ws.counters + 2)) return;
-  if (threadIdx.x == 0) backsub_tail(C, ws);
+  block_partial(s_t, 4, 4, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 4);  // ba_finish_kernel(2) goes on from here
 }
 
 // ---- after the reduction, one thread: the 2-D sub-problem in an orthonormal basis of span{g_h, gn_h}
@@ -1396,10 +1358,7 @@ ba_step_kernel(const double* __restrict__ intr, const double2* __restrict__ pts_
     s_t[warp * 3 + 1] = stepsq;
     s_t[warp * 3 + 2] = xsq;
   }
-  block_partial(s_t, 3, 3, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 3);
-  if (ws.sharded) return;
-  if (!reduce_partials_last_block(ws.partials, 3, 3, ws.red, ws.counters + 3)) return;
-  if (threadIdx.x == 0) step_tail(C, ws, s_cn);
+  block_partial(s_t, 3, 3, ws.partials + (size_t)(blockIdx.x + ws.vb0) * 3);  // ba_finish_kernel(3) goes on from here
 }
 
 // ---- after the reduction, one thread: trf_no_bounds' inner loop body after f_new = fun(x_new); s_cn = the candidate cameras
@@ -1465,25 +1424,54 @@ __global__ void ba_apply_points_kernel(int n, int iter, BAWorkspace ws, double* 
   }
 }
 
-// Frame-sharded runs: what the last block of a per-point pass does on one GPU, after the caller has all-gathered the
-// per-block partials of every rank.  One block.  pass 0 gradient, 1 Schur system, 2 back-substitution, 3 step.
+// Behind every per-point pass (and, frame-sharded, behind the all-gather of the partials of every rank): the fixed-order
+// sum over ALL blocks, one entry of the reduced vector per thread; the last block to finish runs the scalar logic of the
+// pass.  pass 0 gradient, 1 Schur system, 2 back-substitution, 3 step.  grid = ceil(entries / kBAThreads).
 __global__ void __launch_bounds__(kBAThreads) ba_finish_kernel(int pass, int C, BAWorkspace ws) {
   __shared__ double s_cn[kMaxN];
+  __shared__ bool s_last;
   BAState* st = ws.state;
   if (st->done) return;
   if (pass != 3 && !st->need_lin) return;
   if (pass == 1 && st->solver == 1) return;
+  const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
+  const int n_sum = pass == 0 ? n - 1 : n;
+  const int e = blockIdx.x * kBAThreads + threadIdx.x;
+  if (e < n) {
+    const double* part = ws.partials + e;
+    double acc = e < n_sum ? 0.0 : -1.0;
+    // (eight loads in flight, added in block order: the sum stays the one the order defines)
+    int b = 0;
+    for (; b + 8 <= ws.vgrid; b += 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(part + (size_t)(b + k) * n);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = e < n_sum ? acc + v[k] : fmax(acc, v[k]);
+    }
+    for (; b < ws.vgrid; ++b) {
+      const double v = __ldcg(part + (size_t)b * n);
+      acc = e < n_sum ? acc + v : fmax(acc, v);
+    }
+    ws.red[e] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ws.counters + pass, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;   // (state is only written below, after every block has read it above and taken its ticket)
+  __threadfence();
   if (pass == 3) {  // the candidate cameras, as ba_step_kernel builds them
     const double cg = st->coef_g, cn = st->coef_gn;
     if (threadIdx.x < 6 * C)
       s_cn[threadIdx.x] = ws.cam[threadIdx.x] + (cg * ws.ghc[threadIdx.x] + cn * ws.gnc[threadIdx.x]) / ws.sinv_c[threadIdx.x];
+    __syncthreads();
   }
-  const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
-  const int n_sum = pass == 0 ? n - 1 : n;
-  sum_block_partials(ws.partials, n_sum, n, ws.red, (unsigned)ws.vgrid);
-  __threadfence();
-  __syncthreads();
   if (threadIdx.x != 0) return;
+  ws.counters[pass] = 0u;
   if (pass == 0) gradient_tail(C, ws);
   if (pass == 2) backsub_tail(C, ws);
   if (pass == 3) step_tail(C, ws, s_cn);
@@ -1533,6 +1521,11 @@ reprojection_error_kernel(const double* __restrict__ cam_rt, const double* __res
   }
 }
 
+static int ba_finish_grid(int pass, int C) {
+  const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
+  return ceil_div(n, kBAThreads);
+}
+
 static int check_common(const char* fn, int C, int T, int J) {
   DF3D_REQUIRE(C >= 1 && C <= DF3D_MAX_CAMS, DF3D_EINVAL, "%s: C must be in [1,%d]", fn, DF3D_MAX_CAMS);
   DF3D_REQUIRE(T >= 1 && J >= 1 && (long long)T * J * 3 < (1ll << 31), DF3D_EINVAL, "%s: bad T/J", fn);
@@ -1550,7 +1543,7 @@ extern "C" size_t df3d_bundle_adjust_workspace_bytes(int C, int T, int J) {
 
 extern "C" int df3d_bundle_adjust_launches(const df3d_ba_opts* opts) {
   const int iters = opts ? opts->max_iters : 20;
-  const int per_iter = (opts && opts->solver == 0) ? 6 : 5;  // gradient, (schur, solve | lsmr), backsub, step, apply
+  const int per_iter = (opts && opts->solver == 0) ? 10 : 8;  // gradient, finish, (schur, finish, solve | lsmr), backsub, finish, step, finish, apply
   return 2 + per_iter * iters;
 }
 
@@ -1602,16 +1595,20 @@ extern "C" int df3d_bundle_adjust(double* cam_rt_dev, const double* intr_dev, co
   // fixed launch sequence; kernels become no-ops once the device-side state says `done`
   for (int it = 0; it < o.max_iters; ++it) {
     ba_gradient_kernel<<<grid, kBAThreads, smem_g, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_finish_kernel<<<ba_finish_grid(0, C), kBAThreads, 0, s>>>(0, C, ws);
     if (o.solver == 1) {
       void* args[] = {(void*)&intr_dev, (void*)&xy, (void*)&pts3d_dev, (void*)&C, (void*)&TJ, (void*)&ws, (void*)&lsmr_tol,
                       (void*)&lsmr_tol, (void*)&lsmr_conlim, (void*)&lsmr_maxiter};
       DF3D_CUDA(cudaLaunchCooperativeKernel((const void*)ba_lsmr_kernel, dim3(lsmr_grid), dim3(kBAThreads), args, smem_l, s));
     } else {
       ba_schur_kernel<<<grid, kBAThreads, smem_s, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+      ba_finish_kernel<<<ba_finish_grid(1, C), kBAThreads, 0, s>>>(1, C, ws);
       ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
     }
     ba_backsub_kernel<<<grid, kBAThreads, smem_b, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_finish_kernel<<<ba_finish_grid(2, C), kBAThreads, 0, s>>>(2, C, ws);
     ba_step_kernel<<<grid, kBAThreads, smem_e, s>>>(intr_dev, xy, pts3d_dev, C, TJ, ws);
+    ba_finish_kernel<<<ba_finish_grid(3, C), kBAThreads, 0, s>>>(3, C, ws);
     ba_apply_points_kernel<<<agrid, 256, 0, s>>>(n3, it + 1, ws, pts3d_dev, 0);
     DF3D_LAUNCH_CHECK("bundle adjustment iteration");
   }
@@ -1702,7 +1699,7 @@ extern "C" int df3d_ba_sharded_finish(int pass, int iter, int rank, int world, d
   if (int e = ba_sharded_ws("df3d_ba_sharded_finish", C, T, J, workspace_dev, workspace_bytes, rank, world, &ws, &nb)) return e;
   DF3D_REQUIRE(pass >= 0 && pass <= 3 && pts3d_dev, DF3D_EINVAL, "df3d_ba_sharded_finish: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ba_finish_kernel<<<1, kBAThreads, 0, s>>>(pass, C, ws);
+  ba_finish_kernel<<<ba_finish_grid(pass, C), kBAThreads, 0, s>>>(pass, C, ws);
   if (pass == 1) ba_solve_kernel<<<1, kSolveThreads, 0, s>>>(C, ws);
   if (pass == 3) {
     const int n3 = T * J * 3;

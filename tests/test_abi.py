@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu(lib_built):
     d_bad = _lib.HGDesc(8, 19, 250, 256, 4)
     assert lib.df3d_hg_param_count(ctypes.byref(d_bad)) == 0
     assert lib.df3d_bundle_adjust_workspace_bytes(7, 15, 38) > 0
-    assert lib.df3d_bundle_adjust_launches(None) == 2 + 5 * 20          # default solver: LSMR (one cooperative kernel per evaluation)
+    assert lib.df3d_bundle_adjust_launches(None) == 2 + 8 * 20          # default solver: LSMR (per evaluation: 3 passes + their finishes, one cooperative LSMR kernel, apply)
 
 
 def test_flatten_matches_param_count(lib_built):

@@ -6,8 +6,7 @@ grep -E "passed|failed|FAILED|ERROR|differ|Error" gpurun_out/ba_pytest.log | tai
 if [ "$(python -c 'import torch; print(torch.cuda.device_count())')" -ge 2 ]; then
   timeout -s KILL 600 python -m pytest tests/test_gpu_core.py -q -m gpu --no-header -rA -s -k "sharded_two" > gpurun_out/ba_pytest_n2.log 2>&1; echo "pytest n2 exit=$?"
   grep -E "passed|failed|FAILED|ERROR|differ|Error" gpurun_out/ba_pytest_n2.log | tail -15
-  timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/ba_bench_n2.log 2> gpurun_out/ba_bench_n2.err; echo "bench n2 exit=$?"
-  tail -1 gpurun_out/ba_bench_n2.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['bundle_adjust'], d['gpu_launches'])" || tail -5 gpurun_out/ba_bench_n2.err
+  timeout -s KILL 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/ba_sharded_time.py 8000 2>&1 | grep "^T=" | tee gpurun_out/ba_sharded_time.txt
 fi
+timeout -s KILL 100 python tools/ba_sharded_time.py 8000 2>&1 | grep "^T=" | tee -a gpurun_out/ba_sharded_time.txt
+timeout -s KILL 100 python tools/ba_time.py 256 1000 8000 2>&1 | grep "^T=" | tee gpurun_out/ba_time.txt

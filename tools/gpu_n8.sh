@@ -14,5 +14,4 @@ PY
 }
 timeout -s KILL 300 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline --no-files > gpurun_out/n8_bench_n1.log 2> gpurun_out/n8_bench_n1.err; echo "config2 N=1 exit=$?"; show gpurun_out/n8_bench_n1.log
 timeout -s KILL 400 $TR --master-port 29521 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/n8_bench_c2.log 2> gpurun_out/n8_bench_c2.err; echo "config2 N=8 exit=$?"; show gpurun_out/n8_bench_c2.log
-DF3D_BENCH_BA_MAX_FRAMES=1000 timeout -s KILL 400 $TR --master-port 29523 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/n8_bench_c2_bacap.log 2> gpurun_out/n8_bench_c2_bacap.err; echo "config2 N=8, BA capped exit=$?"; show gpurun_out/n8_bench_c2_bacap.log
 timeout -s KILL 600 $TR --master-port 29522 bench.py --gpus 8 --config 4 --steps 2 --warmup 3 > gpurun_out/n8_bench_c4.log 2> gpurun_out/n8_bench_c4.err; echo "config4 N=8 exit=$?"; show gpurun_out/n8_bench_c4.log; tail -3 gpurun_out/n8_bench_c4.err
