@@ -250,9 +250,9 @@ __device__ __forceinline__ void point_M(unsigned mask, const double (&V)[3][3], 
   }
 }
 
-// Every per-point pass ends with one partial vector per block (block_partial); ba_finish_kernel sums the blocks in block
-// order -- entries [0, n_sum) are summed, [n_sum, n) take the maximum -- one entry per thread, and its last block runs the
-// scalar logic that follows the pass.  (Round 2 first summed inside the last block of the pass itself: 592 blocks x
+// Every per-point pass ends with one partial vector per block (block_partial); ba_finish_kernel sums the blocks in a
+// fixed order -- entries [0, n_sum) are summed, [n_sum, n) take the maximum --, and its last block runs the scalar logic
+// that follows the pass.  (Round 2 first summed inside the last block of the pass itself: 592 blocks x
 // 2 102 doubles through ONE block cost ~0.6 ms per evaluation at 8 000 frames, two thirds of the whole solve.)
 // block partial = fixed-order sum (or max) of the per-warp tiles
 __device__ __forceinline__ void block_partial(const double* s_tiles, int n_sum, int n, double* part) {
@@ -1424,11 +1424,16 @@ __global__ void ba_apply_points_kernel(int n, int iter, BAWorkspace ws, double* 
   }
 }
 
-// Behind every per-point pass (and, frame-sharded, behind the all-gather of the partials of every rank): the fixed-order
-// sum over ALL blocks, one entry of the reduced vector per thread; the last block to finish runs the scalar logic of the
-// pass.  pass 0 gradient, 1 Schur system, 2 back-substitution, 3 step.  grid = ceil(entries / kBAThreads).
+// Behind every per-point pass (and, frame-sharded, behind the all-gather of the partials of every rank): the sum over ALL
+// blocks in a fixed order that depends on the number of blocks only -- kFinChunks runs of consecutive blocks per entry,
+// each summed in block order by one thread (eight loads in flight), the runs then added in run order --, 16 entries per
+// block of 128 threads; the last block to finish runs the scalar logic of the pass.  pass 0 gradient, 1 Schur system,
+// 2 back-substitution, 3 step.  grid = ceil(entries / kFinEntries).
+constexpr int kFinChunks = 8, kFinEntries = kBAThreads / kFinChunks;
+
 __global__ void __launch_bounds__(kBAThreads) ba_finish_kernel(int pass, int C, BAWorkspace ws) {
   __shared__ double s_cn[kMaxN];
+  __shared__ double s_run[kFinChunks][kFinEntries];
   __shared__ bool s_last;
   BAState* st = ws.state;
   if (st->done) return;
@@ -1436,24 +1441,34 @@ __global__ void __launch_bounds__(kBAThreads) ba_finish_kernel(int pass, int C, 
   if (pass == 1 && st->solver == 1) return;
   const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
   const int n_sum = pass == 0 ? n - 1 : n;
-  const int e = blockIdx.x * kBAThreads + threadIdx.x;
+  const int el = threadIdx.x % kFinEntries, run = threadIdx.x / kFinEntries;
+  const int e = blockIdx.x * kFinEntries + el;
+  const int len = (ws.vgrid + kFinChunks - 1) / kFinChunks;
+  const int b0 = run * len, b1 = min(ws.vgrid, b0 + len);
+  const bool is_sum = e < n_sum;
+  double acc = is_sum ? 0.0 : -1.0;
   if (e < n) {
     const double* part = ws.partials + e;
-    double acc = e < n_sum ? 0.0 : -1.0;
-    // (eight loads in flight, added in block order: the sum stays the one the order defines)
-    int b = 0;
-    for (; b + 8 <= ws.vgrid; b += 8) {
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
       double v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = __ldcg(part + (size_t)(b + k) * n);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = e < n_sum ? acc + v[k] : fmax(acc, v[k]);
+      for (int k = 0; k < 8; ++k) acc = is_sum ? acc + v[k] : fmax(acc, v[k]);
     }
-    for (; b < ws.vgrid; ++b) {
+    for (; b < b1; ++b) {
       const double v = __ldcg(part + (size_t)b * n);
-      acc = e < n_sum ? acc + v : fmax(acc, v);
+      acc = is_sum ? acc + v : fmax(acc, v);
     }
-    ws.red[e] = acc;
+  }
+  s_run[run][el] = acc;
+  __syncthreads();
+  if (run == 0 && e < n) {
+    double tot = s_run[0][el];
+#pragma unroll
+    for (int r = 1; r < kFinChunks; ++r) tot = is_sum ? tot + s_run[r][el] : fmax(tot, s_run[r][el]);
+    ws.red[e] = tot;
   }
   __threadfence();
   __syncthreads();
@@ -1523,7 +1538,7 @@ reprojection_error_kernel(const double* __restrict__ cam_rt, const double* __res
 
 static int ba_finish_grid(int pass, int C) {
   const int n = pass == 0 ? g_doubles(C) : pass == 1 ? sys_doubles(C) : pass == 2 ? 4 : 3;
-  return ceil_div(n, kBAThreads);
+  return ceil_div(n, kFinEntries);
 }
 
 static int check_common(const char* fn, int C, int T, int J) {
