@@ -8,24 +8,28 @@
 // problems (scipy/optimize/_lsq/trf.py::trf_no_bounds, the tr_solver == 'lsmr' branch) statement by
 // statement, with one substitution: the regularised Gauss-Newton step that SciPy gets from LSMR,
 //     gn_h = argmin |J_h p - f|^2 + reg |p|^2 ,   J_h = J diag(1 / column norm),
-// is solved exactly through the Schur complement on the 6C camera unknowns.  Measured on the CPU
-// prototype (tools/ba_proto.py): 1-2e-5 mm from SciPy at T = 15 ... 1000 frames -- the distance between
-// SciPy with its default LSMR tolerance and SciPy with a converged LSMR.
+// is either that LSMR iteration itself, restated on the device (solver 1, ba_lsmr_kernel: what reproduces the
+// reference's golden file to 1.3e-6 mm), or solved exactly through the Schur complement on the 6C camera unknowns
+// (solver 0: 1-2e-5 mm from SciPy at T = 15 ... 1000 frames -- the distance between SciPy with its default LSMR
+// tolerance and SciPy with a converged LSMR; tools/ba_proto.py is the CPU prototype).
 //
 // One outer iteration = a fixed sequence of launches, no host synchronisation (device-side flags turn the
-// kernels into no-ops once the solver has terminated, and skip the linearisation after a rejected step):
+// kernels into no-ops once the solver has terminated, and skip the linearisation after a rejected step).  Every
+// per-point pass leaves one partial vector per block of 128 points (warp shuffles -> per-warp shared-memory tiles
+// with a single writer -> block partial); ba_finish sums the blocks in an order fixed by the block count alone and
+// its last block runs the scalar logic of the pass: bit-reproducible, and independent of how the blocks were spread
+// over GPUs (df3d_ba_sharded_*: each rank runs a slice of the blocks, the caller all-gathers the partials).
 //   ba_gradient : one thread per 3-D point.  Analytic Jacobian (Rodrigues + pin-hole); gradient, column
 //                 norms (Jacobi scaling, running maximum like compute_jac_scale), cost, and the pieces of
-//                 |J_h g_h|^2; the last block derives the Cauchy-step regularisation `reg`
+//                 |J_h g_h|^2; finish: the Cauchy-step regularisation `reg`
 //   ba_schur    : one thread per point.  Per-point M = D_p (D_p V D_p + reg I)^-1 D_p; reduced system
-//                 S~ = sum W M W^T,  b~ = sum W M g_p  (warp shuffles -> per-warp shared-memory tiles with a
-//                 single writer -> per-block partials -> fixed-order sum by the last block: bit-reproducible)
+//                 S~ = sum W M W^T,  b~ = sum W M g_p
 //   ba_solve    : one CTA.  D_c (U - S~) D_c + reg I, Cholesky + one refinement step -> camera part of gn_h
-//   ba_backsub  : one thread per point.  Point part of gn_h, the Gram quantities of span{g_h, gn_h}; the last
-//                 block builds the 2-D sub-problem and solves it inside the trust region
-//   ba_step     : one thread per point.  Candidate x + D step_h, its cost; the last block runs SciPy's
-//                 ratio test, radius update and termination rule, and re-solves the 2-D problem after a
-//                 rejected step
+//                 (solver 1: ba_lsmr instead of ba_schur + ba_solve)
+//   ba_backsub  : one thread per point.  Point part of gn_h, the Gram quantities of span{g_h, gn_h}; finish:
+//                 the 2-D sub-problem, solved inside the trust region
+//   ba_step     : one thread per point.  Candidate x + D step_h, its cost; finish: SciPy's ratio test, radius
+//                 update and termination rule, and the 2-D problem again after a rejected step
 //   ba_apply    : copies the candidate points after an accepted step
 #include <cooperative_groups.h>
 
@@ -36,7 +40,7 @@ namespace df3d {
 
 constexpr int kBAThreads = 128;
 constexpr int kBAWarps = kBAThreads / 32;
-constexpr int kBAMaxBlocks = 4 * 148;  // per-block partials are summed by the last block in block order: bounded, but enough
+constexpr int kBAMaxBlocks = 4 * 148;  // one partial vector per block, summed by ba_finish_kernel: bounded, but enough
                                       // blocks to keep several per SM in flight (the passes are fp64 latency-bound)
 constexpr int kMaxN = 6 * DF3D_MAX_CAMS;
 constexpr int kLsmrRed = 64;  // values of one grid-wide reduction of the LSMR kernel (2 scalars + 6 C camera sums, padded)
@@ -69,7 +73,7 @@ __host__ __device__ inline int off_cost(int C) { return 48 * C + 36 * C * C; }
 
 struct BAWorkspace {  // carved out of the caller's buffer
   BAState* state;
-  unsigned int* counters;  // last-block tickets, one per reducing kernel
+  unsigned int* counters;  // last-block tickets of ba_finish_kernel, one per pass
   double* cam;             // C*6 current cameras
   double* sinv_c;          // C*6 camera column norms (running maximum)
   double* gc;              // C*6 camera gradient
@@ -90,9 +94,9 @@ struct BAWorkspace {  // carved out of the caller's buffer
   double* lhb;             // TJ*3
   double* lpart;           // 2 * kBAMaxBlocks * kLsmrRed
   // Block space of the per-point passes: a launch covers the virtual blocks [vb0, vb0 + gridDim.x) of `vgrid`.  One GPU:
-  // vb0 = 0, gridDim.x = vgrid and the last block to finish sums the per-block partials.  Frame-sharded (`sharded`): each
-  // rank launches its own slice of the blocks, the caller all-gathers the partials and ba_finish_kernel does the sum --
-  // same blocks, same order, same bits as on one GPU.
+  // vb0 = 0 and gridDim.x = vgrid.  Frame-sharded (`sharded`): each
+  // rank launches its own slice of the blocks and the caller all-gathers the partials before ba_finish_kernel sums them
+  // -- same blocks, same order, same bits as on one GPU.
   int vb0, vgrid, sharded, pad;
 };
 

@@ -48,6 +48,21 @@ def test_argument_validation_without_gpu(lib_built):
     assert lib.df3d_bundle_adjust_launches(None) == 2 + 8 * 20          # default solver: LSMR (per evaluation: 3 passes + their finishes, one cooperative LSMR kernel, apply)
 
 
+def test_sharded_bundle_adjust_plan_is_a_host_function(lib_built):
+    """df3d_ba_sharded_plan needs no GPU: block count, where the per-block partial sums live in the workspace, doubles per
+    block of the four passes; block counts that do not split evenly over the ranks are refused."""
+    from deepfly3d_b200 import _lib, ops
+
+    nb, off, pd = ops.ba_sharded_plan(7, 8000, 38, 8)
+    assert nb == 4 * 148 and nb % 8 == 0                      # 304 000 points / 128 per block, capped
+    assert off % 256 == 0 and 0 < off < _lib.lib.df3d_bundle_adjust_workspace_bytes(7, 8000, 38)
+    assert pd == [36 * 7 + 12 * 7 + 6, 36 * 7 + 6 * 7 + 36 * 49 + 6 * 7 + 2, 4, 3]
+    assert off + nb * max(pd) * 8 <= _lib.lib.df3d_bundle_adjust_workspace_bytes(7, 8000, 38)
+    assert ops.ba_sharded_plan(7, 26, 38, 2)[0] == 8          # 988 points -> 8 blocks
+    assert ops.ba_sharded_plan(7, 26, 38, 3) is None          # 8 blocks over 3 ranks
+    assert ops.ba_sharded_plan(7, 3, 38, 4) is None           # 1 block over 4 ranks
+
+
 def test_flatten_matches_param_count(lib_built):
     from deepfly3d_b200 import _lib, hourglass
     from oracle import hourglass as ohg
