@@ -49,6 +49,15 @@ def block_frames_for(in_h, in_w, T, batch_size=8):
     return max(1, min(int(T), images // NUM_CAMERAS))
 
 
+def stream_block_frames(engine_block, gpu_decode=False):
+    """Frames per streamed block when the caller did not choose: with the host decode -- the slower side of the stream --
+    quarter-size blocks start the GPU earlier (the first block is the only one whose decode nothing hides) and still
+    fill it (measured on 256 frames of 480x960 JPEGs, 16 host cores: 128-frame blocks 698, 64-frame 808, 32-frame 949
+    frames/s through pose2d_estimation); the device decode takes whole engine blocks."""
+    engine_block = int(engine_block)
+    return engine_block // 4 if (not gpu_decode and engine_block >= 32) else engine_block
+
+
 class FolderReader:
     """Threaded host-side read of ``camera_{c}_img_{t}.jpg`` frame blocks (native size, gray)."""
 
@@ -325,12 +334,7 @@ def inference_folder(folder, camera_ids_to_flip=(), return_heatmap=False, return
     Hh, Wh = HEATMAP_SHAPE
     in_h, in_w = input_size if input_size is not None else (4 * Hh, 4 * Wh)
     T = max_img_id + 1
-    bf = int(block_frames) if block_frames else block_frames_for(in_h, in_w, T, batch_size)
-    if not block_frames and not gpu_decode and bf >= 32:
-        # host decode is the slower side of the stream: quarter-size blocks start the GPU earlier (the first block is
-        # the only one whose decode nothing hides) and still fill it (measured on 256 frames of 480x960 JPEGs, 16 host
-        # cores: 128-frame blocks 698, 64-frame 808, 32-frame 949 frames/s through pose2d_estimation)
-        bf //= 4
+    bf = int(block_frames) if block_frames else stream_block_frames(block_frames_for(in_h, in_w, T, batch_size), gpu_decode)
     blocks = plan_blocks(T, bf)
     dev = torch.device(device)
     eng = get_engine(state_dict, in_h, in_w, NUM_CAMERAS * bf, device=device, mean=load_mean(mean), weights=weights)

@@ -65,3 +65,19 @@ def test_video_reader_streams_frames_in_order(tmp_path):
     expect = 16 + 32 * np.arange(7)[:, None] + 3 * np.arange(T)[None, :]
     assert np.abs(seen - expect).max() <= 3.5                              # lossy codec (limited-range YUV), flat frames
     assert np.all(np.diff(seen, axis=1) > 0) and np.all(np.diff(seen, axis=0) > 0)   # frame and camera order
+
+
+def test_block_plan_of_the_streaming_loader():
+    """Host logic of inference_folder: engine block from the input size (1 792 images at 256 x 256, scaled by area, never
+    below the reference's batch_size), quarter-size blocks for the host decode, blocks covering [0, T) in order."""
+    from deepfly3d_b200 import inference
+
+    assert inference.block_frames_for(256, 256, 1000) == 256
+    assert inference.block_frames_for(256, 512, 1000) == 128
+    assert inference.block_frames_for(256, 512, 3) == 3                      # never more than the recording
+    assert inference.block_frames_for(2048, 2048, 1000, batch_size=8) == 4   # 28 images: 4 whole frames
+    assert inference.block_frames_for(2048, 2048, 1000, batch_size=64) == 9  # a larger batch_size raises the block
+    assert inference.stream_block_frames(128) == 32 and inference.stream_block_frames(128, gpu_decode=True) == 128
+    assert inference.stream_block_frames(3) == 3
+    assert inference.plan_blocks(10, 4) == [(0, 4), (4, 8), (8, 10)]
+    assert inference.plan_blocks(0, 4) == []
